@@ -1,0 +1,709 @@
+// cgb_api.cu -- C ABI of libcgb200.so (see include/cgb200.h). Host-side bookkeeping + kernel launches.
+// There is no CPU path here: without a CUDA device cgb_create fails with CGB_ERR_NO_DEVICE.
+#include "cgb_handle.h"
+#include "cgb_euler.cuh"
+#include "cgb_lite.cuh"
+#include "cgb_salt.cuh"
+
+using namespace cgb;
+
+static thread_local std::string g_create_error;
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int cgb_abi_version(void) { return CGB_ABI_VERSION; }
+
+extern "C" const char* cgb_last_error(const cgb_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int cgb_create(const cgb_config* cfg, cgb_handle** out)
+{
+    if (!cfg || !out) { g_create_error = "null argument"; return CGB_ERR_INVALID; }
+    *out = nullptr;
+    if (cfg->abi_version != CGB_ABI_VERSION) { g_create_error = "ABI version mismatch"; return CGB_ERR_INVALID; }
+    if (cfg->n_cells < 2 || cfg->n_columns < 1 || cfg->n_layers < 1 || cfg->n_layers > 64) {
+        g_create_error = "need n_cells >= 2, n_columns >= 1, 1 <= n_layers <= 64";
+        return CGB_ERR_INVALID;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device available (libcgb200 has no CPU fallback): ") + cudaGetErrorString(e);
+        return CGB_ERR_NO_DEVICE;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "device ordinal out of range"; return CGB_ERR_INVALID; }
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return CGB_ERR_CUDA; }
+    cudaDeviceProp prop{};
+    cudaGetDeviceProperties(&prop, cfg->device);
+    if (prop.major != 10) {
+        g_create_error = "libcgb200 is built for sm_100a only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+        return CGB_ERR_NO_DEVICE;
+    }
+    int cpl_needed = (cfg->n_cells + 31) / 32;
+    if (cpl_needed > 16) { g_create_error = "n_cells > 512 is not supported by the warp-per-column kernels"; return CGB_ERR_UNSUPPORTED; }
+    cgb_handle* h = new cgb_handle();
+    h->cfg = *cfg;
+    h->N = cfg->n_cells; h->M = cfg->n_columns; h->nl = cfg->n_layers;
+    h->nvar = (cfg->physics == CGB_PHYSICS_HEAT_SALT) ? 2 : 1;
+    h->num_sms = prop.multiProcessorCount;
+    h->fc_kind.assign(h->nl, CGB_FC_FREEWATER);
+    h->fc_solver.assign(h->nl, CGB_SOLVER_LUT);
+    h->cell_layer.assign(h->N, 0);
+    cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2; ++i) {
+        cudaEventCreateWithFlags(&h->stage_ready[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&h->stage_free[i], cudaEventDisableTiming);
+    }
+    // defaults: thermal_properties.jl:13-18, Soils/para/simple.jl:37-43, Physics.jl:3-8
+    auto setg = [&](const char* n, double v) { h->params[n].v = {v}; h->params[n].per = CGB_PER_GLOBAL; };
+    setg("kh_w", 0.57); setg("kh_i", 2.2); setg("kh_a", 0.025); setg("kh_m", 3.8); setg("kh_o", 0.25);
+    setg("ch_w", 4.2e6); setg("ch_i", 1.9e6); setg("ch_a", 0.00125e6); setg("ch_m", 2.0e6); setg("ch_o", 2.5e6);
+    setg("L", 3.34e8);
+    setg("por", 0.5); setg("sat", 1.0); setg("org", 0.0);
+    setg("vg_alpha", 1.0); setg("vg_n", 2.0); setg("theta_res", 0.0); setg("Tm", 0.0); setg("beta", 1.0); setg("omega", 1.0);
+    setg("nf", 1.0); setg("nt", 1.0); setg("top_offset", 0.0);
+    setg("tau", 1.5); setg("ds0", 8.0e-10); setg("benthic_salt", 900.0); setg("salt_dc_max", 5.0e-3); setg("salt_para_por", 0.5);
+    setg("salt_surface_state", 0.0);
+    // device state
+    size_t nu = (size_t)h->nvar * h->N * h->M;
+    int rc = 0;
+    rc |= dev_alloc(h, &h->dev.u, nu);
+    rc |= dev_alloc(h, &h->dev.t, (size_t)h->M);
+    rc |= dev_alloc(h, &h->dev.dt, (size_t)h->M);
+    rc |= dev_alloc(h, &h->dev.steps, (size_t)h->M);
+    rc |= dev_alloc(h, &h->dev.iters, (size_t)h->M);
+    rc |= dev_alloc(h, &h->dev.status, (size_t)h->M);
+    rc |= dev_alloc(h, &h->dev.counter, 1);
+    rc |= dev_alloc(h, &h->d_scratch, (size_t)cgb_handle::kScratch * (h->N + 1) * h->M);
+    if (rc) { g_create_error = h->err; cgb_destroy(h); return rc; }
+    h->n_state_allocs = h->allocs.size();
+    *out = h;
+    return CGB_OK;
+}
+
+extern "C" void cgb_destroy(cgb_handle* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    for (void* p : h->allocs) cudaFree(p);
+    for (int i = 0; i < 2; ++i) {
+        if (h->d_stage[i]) cudaFree(h->d_stage[i]);
+        if (i == 0 && h->d_lite) cudaFree(h->d_lite);
+        if (h->stage_ready[i]) cudaEventDestroy(h->stage_ready[i]);
+        if (h->stage_free[i]) cudaEventDestroy(h->stage_free[i]);
+    }
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    delete h;
+}
+
+extern "C" int cgb_set_grid(cgb_handle* h, const double* edges)
+{
+    if (!h || !edges) return CGB_ERR_INVALID;
+    for (int i = 0; i < h->N; ++i)
+        if (!(edges[i + 1] > edges[i])) CGB_FAIL(h, CGB_ERR_INVALID, "grid edges must be strictly increasing (edge %d)", i);
+    h->edges.assign(edges, edges + h->N + 1);
+    h->dirty = true;
+    return CGB_OK;
+}
+
+extern "C" int cgb_set_layers(cgb_handle* h, const int32_t* cell_layer)
+{
+    if (!h || !cell_layer) return CGB_ERR_INVALID;
+    for (int i = 0; i < h->N; ++i) {
+        if (cell_layer[i] < 0 || cell_layer[i] >= h->nl) CGB_FAIL(h, CGB_ERR_INVALID, "cell_layer[%d]=%d out of range", i, cell_layer[i]);
+        if (i > 0 && cell_layer[i] < cell_layer[i - 1]) CGB_FAIL(h, CGB_ERR_INVALID, "cell_layer must be non-decreasing");
+    }
+    h->cell_layer.assign(cell_layer, cell_layer + h->N);
+    h->dirty = true;
+    return CGB_OK;
+}
+
+extern "C" int cgb_set_param(cgb_handle* h, const char* name, const double* values, int64_t n, int32_t per)
+{
+    if (!h || !name || !values) return CGB_ERR_INVALID;
+    auto it = h->params.find(name);
+    bool is_bot = std::strcmp(name, "bot_value") == 0;
+    if (it == h->params.end() && !is_bot) CGB_FAIL(h, CGB_ERR_INVALID, "unknown parameter '%s'", name);
+    int64_t want = -1;
+    switch (per) {
+    case CGB_PER_GLOBAL: want = 1; break;
+    case CGB_PER_LAYER: want = h->nl; break;
+    case CGB_PER_COLUMN: want = h->M; break;
+    case CGB_PER_COLUMN_LAYER: want = (int64_t)h->nl * h->M; break;
+    case CGB_PER_CELL: want = h->N; break;
+    default: CGB_FAIL(h, CGB_ERR_INVALID, "bad granularity %d", per);
+    }
+    if (n != want) CGB_FAIL(h, CGB_ERR_INVALID, "parameter '%s': expected %lld values, got %lld", name, (long long)want, (long long)n);
+    ParamArray& p = h->params[name];
+    p.v.assign(values, values + n);
+    p.per = per;
+    h->dirty = true;
+    return CGB_OK;
+}
+
+extern "C" int cgb_set_freezecurve(cgb_handle* h, int32_t layer, int32_t fc_kind, int32_t solver)
+{
+    if (!h) return CGB_ERR_INVALID;
+    if (layer < 0 || layer >= h->nl) CGB_FAIL(h, CGB_ERR_INVALID, "layer %d out of range", layer);
+    if (fc_kind < 0 || fc_kind > 3 || solver < 0 || solver > 1) CGB_FAIL(h, CGB_ERR_INVALID, "bad freeze curve / solver");
+    h->fc_kind[layer] = fc_kind;
+    h->fc_solver[layer] = solver;
+    h->dirty = true;
+    return CGB_OK;
+}
+
+extern "C" int cgb_set_sfcc_table(cgb_handle* h, int32_t table_id, const double* Hk, const double* Tk, int64_t nk, int32_t extrap)
+{
+    if (!h || !Hk || !Tk) return CGB_ERR_INVALID;
+    if (table_id < 0 || table_id >= 65536 || nk < 2) CGB_FAIL(h, CGB_ERR_INVALID, "bad table id or length");
+    for (int64_t i = 1; i < nk; ++i)
+        if (!(Hk[i] > Hk[i - 1])) CGB_FAIL(h, CGB_ERR_INVALID, "table knots must be strictly increasing");
+    LutTable& t = h->tables[table_id];
+    t.H.assign(Hk, Hk + nk);
+    t.T.assign(Tk, Tk + nk);
+    t.extrap = extrap;
+    h->dirty = true;
+    return CGB_OK;
+}
+
+extern "C" int cgb_set_sfcc_table_map(cgb_handle* h, const int32_t* map)
+{
+    if (!h) return CGB_ERR_INVALID;
+    if (map) h->table_map.assign(map, map + (size_t)h->nl * h->M); else h->table_map.clear();
+    h->dirty = true;
+    return CGB_OK;
+}
+
+extern "C" int cgb_set_forcing_table(cgb_handle* h, int32_t which, const double* t, const double* y, int64_t n)
+{
+    if (!h || !t || !y || which < 0 || which > 1) return CGB_ERR_INVALID;
+    if (n < 2) CGB_FAIL(h, CGB_ERR_INVALID, "forcing table needs >= 2 knots");
+    for (int64_t i = 1; i < n; ++i)
+        if (!(t[i] > t[i - 1])) CGB_FAIL(h, CGB_ERR_INVALID, "forcing times must be strictly increasing");
+    auto& f = h->forc[which];
+    f.kind = 2; f.t.assign(t, t + n); f.y.assign(y, y + n);
+    h->dirty = true;
+    return CGB_OK;
+}
+
+extern "C" int cgb_set_forcing_periodic(cgb_handle* h, int32_t which, double period, double amplitude, double phase, double level)
+{
+    if (!h || which < 0 || which > 1) return CGB_ERR_INVALID;
+    auto& f = h->forc[which];
+    f.kind = 1; f.period = period; f.amp = amplitude; f.phase = phase; f.level = level;
+    h->dirty = true;
+    return CGB_OK;
+}
+
+extern "C" int cgb_set_forcing_constant(cgb_handle* h, int32_t which, double value)
+{
+    if (!h || which < 0 || which > 1) return CGB_ERR_INVALID;
+    auto& f = h->forc[which];
+    f.kind = 0; f.value = value;
+    h->dirty = true;
+    return CGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// push the host-side description to the device
+// ------------------------------------------------------------------------------------------------
+static std::vector<double> expand(const cgb_handle* h, const ParamArray& p, int target /* COLUMN or COLUMN_LAYER */)
+{
+    size_t M = (size_t)h->M, nl = (size_t)h->nl;
+    std::vector<double> out(target == CGB_PER_COLUMN ? M : nl * M);
+    if (target == CGB_PER_COLUMN) {
+        for (size_t c = 0; c < M; ++c) out[c] = (p.per == CGB_PER_COLUMN) ? p.v[c] : p.v[0];
+    } else {
+        for (size_t l = 0; l < nl; ++l)
+            for (size_t c = 0; c < M; ++c) {
+                double v;
+                switch (p.per) {
+                case CGB_PER_LAYER: v = p.v[l]; break;
+                case CGB_PER_COLUMN: v = p.v[c]; break;
+                case CGB_PER_COLUMN_LAYER: v = p.v[l * M + c]; break;
+                default: v = p.v[0];
+                }
+                out[l * M + c] = v;
+            }
+    }
+    return out;
+}
+
+static int finalize(cgb_handle* h)
+{
+    if (!h->dirty) return CGB_OK;
+    if ((int)h->edges.size() != h->N + 1) CGB_FAIL(h, CGB_ERR_INVALID, "cgb_set_grid has not been called");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    while (h->allocs.size() > h->n_state_allocs) { cudaFree(h->allocs.back()); h->allocs.pop_back(); }
+    Dev& d = h->dev;
+    const int N = h->N;
+    d.N = N; d.n_layers = h->nl; d.nvar = h->nvar; d.M = h->M;
+    int rc = 0;
+    // grid: Numerics/grid.jl:24-33
+    std::vector<double> zc(N), dk(N), idk(N), dxc(std::max(N - 1, 1)), w1(N + 1, 1.0), w2(N + 1, 1.0), g(N + 1, 0.0);
+    for (int i = 0; i < N; ++i) { zc[i] = (h->edges[i] + h->edges[i + 1]) / 2.0; dk[i] = h->edges[i + 1] - h->edges[i]; idk[i] = 1.0 / dk[i]; }
+    for (int i = 0; i + 1 < N; ++i) dxc[i] = zc[i + 1] - zc[i];
+    for (int e = 1; e < N; ++e) { w1[e] = dk[e - 1]; w2[e] = dk[e]; g[e] = (w1[e] + w2[e]) / dxc[e - 1]; }
+    double *p_dk, *p_idk, *p_dxc, *p_w1, *p_w2, *p_g, *p_zc;
+    rc |= dev_upload(h, &p_dk, dk); rc |= dev_upload(h, &p_idk, idk); rc |= dev_upload(h, &p_dxc, dxc);
+    rc |= dev_upload(h, &p_w1, w1); rc |= dev_upload(h, &p_w2, w2); rc |= dev_upload(h, &p_g, g); rc |= dev_upload(h, &p_zc, zc);
+    d.dk = p_dk; d.inv_dk = p_idk; d.dxc = p_dxc; d.eW1 = p_w1; d.eW2 = p_w2; d.eG = p_g;
+    d.ctop = 1.0 / (dk[0] / 2.0); d.cbot = 1.0 / (dk[N - 1] / 2.0);
+    int* p_cl; rc |= dev_upload(h, &p_cl, h->cell_layer); d.cell_layer = p_cl;
+    int first = N - 1;
+    while (first > 0 && h->cell_layer[first - 1] == h->cell_layer[N - 1]) --first;
+    d.bot_layer_first = first;
+    // freeze curves
+    std::vector<int> kinds(h->nl);
+    bool any_lut = false;
+    for (int l = 0; l < h->nl; ++l) {
+        kinds[l] = h->fc_kind[l] | (h->fc_solver[l] << 8);
+        if (h->fc_kind[l] != CGB_FC_FREEWATER && h->fc_solver[l] == CGB_SOLVER_LUT) any_lut = true;
+    }
+    int* p_k; rc |= dev_upload(h, &p_k, kinds); d.fc_kind = p_k;
+    // LUTs
+    int maxid = -1;
+    for (auto& kv : h->tables) maxid = std::max(maxid, kv.first);
+    std::vector<int> off(std::max(maxid + 1, 1), 0), len(std::max(maxid + 1, 1), 0), ext(std::max(maxid + 1, 1), 0);
+    std::vector<double> allH, allT;
+    for (auto& kv : h->tables) {
+        off[kv.first] = (int)allH.size(); len[kv.first] = (int)kv.second.H.size(); ext[kv.first] = kv.second.extrap;
+        allH.insert(allH.end(), kv.second.H.begin(), kv.second.H.end());
+        allT.insert(allT.end(), kv.second.T.begin(), kv.second.T.end());
+    }
+    if (any_lut) {
+        for (int l = 0; l < h->nl; ++l) {
+            if (h->fc_kind[l] == CGB_FC_FREEWATER || h->fc_solver[l] != CGB_SOLVER_LUT) continue;
+            if (h->table_map.empty()) {
+                if (l > maxid || len[l] < 2) CGB_FAIL(h, CGB_ERR_INVALID, "layer %d uses the SFCC LUT solver but table %d was not set", l, l);
+            } else {
+                for (long long c = 0; c < h->M; ++c) {
+                    int id = h->table_map[(size_t)l * h->M + c];
+                    if (id < 0 || id > maxid || len[id] < 2) CGB_FAIL(h, CGB_ERR_INVALID, "table_map[%d,%lld]=%d refers to a missing table", l, c, id);
+                }
+            }
+        }
+    }
+    double *p_lh, *p_lt; int *p_off, *p_len, *p_ext, *p_map = nullptr;
+    rc |= dev_upload(h, &p_lh, allH); rc |= dev_upload(h, &p_lt, allT);
+    rc |= dev_upload(h, &p_off, off); rc |= dev_upload(h, &p_len, len); rc |= dev_upload(h, &p_ext, ext);
+    if (!h->table_map.empty()) rc |= dev_upload(h, &p_map, h->table_map);
+    d.lutH = p_lh; d.lutT = p_lt; d.lut_off = p_off; d.lut_len = p_len; d.lut_extrap = p_ext; d.table_map = p_map;
+    // per (layer, column) parameters
+    auto up_cl = [&](const char* name, const double** dst) {
+        double* p; std::vector<double> v = expand(h, h->params[name], CGB_PER_COLUMN_LAYER);
+        rc |= dev_upload(h, &p, v); *dst = p;
+    };
+    auto up_c = [&](const char* name, const double** dst) {
+        double* p; std::vector<double> v = expand(h, h->params[name], CGB_PER_COLUMN);
+        rc |= dev_upload(h, &p, v); *dst = p;
+    };
+    up_cl("por", &d.por); up_cl("sat", &d.sat); up_cl("org", &d.org);
+    up_cl("vg_alpha", &d.vg_alpha); up_cl("vg_n", &d.vg_n); up_cl("theta_res", &d.theta_res);
+    up_cl("Tm", &d.Tm); up_cl("beta", &d.beta); up_cl("omega", &d.omega);
+    up_c("nf", &d.nf); up_c("nt", &d.nt); up_c("top_offset", &d.top_offset);
+    d.bot_value = nullptr;
+    if (h->params.count("bot_value")) up_c("bot_value", &d.bot_value);
+    auto G = [&](const char* n) { return h->params[n].v[0]; };
+    d.sk_w = std::sqrt(G("kh_w")); d.sk_i = std::sqrt(G("kh_i")); d.sk_a = std::sqrt(G("kh_a"));
+    d.sk_m = std::sqrt(G("kh_m")); d.sk_o = std::sqrt(G("kh_o"));
+    d.ch_w = G("ch_w"); d.ch_i = G("ch_i"); d.ch_a = G("ch_a"); d.ch_m = G("ch_m"); d.ch_o = G("ch_o");
+    d.L = G("L");
+    d.g = 9.80665; d.Lsl = 3.34e5; d.R = 8.314459; d.rho_w = 1000.0;   // Physics.jl:3-8 ; FreezeCurves defaults
+    // boundary conditions
+    d.top_kind = h->cfg.top_kind; d.bot_kind = h->cfg.bot_kind; d.use_nfactor = h->cfg.use_nfactor; d.limiter = h->cfg.limiter;
+    for (int w = 0; w < 2; ++w) {
+        Forcing F{};
+        auto& f = h->forc[w];
+        F.kind = f.kind; F.value = f.value; F.period = f.period; F.amplitude = f.amp; F.phase = f.phase; F.level = f.level;
+        F.n = (int)f.t.size(); F.t = nullptr; F.y = nullptr;
+        if (f.kind == 2) {
+            double *pt, *py;
+            rc |= dev_upload(h, &pt, f.t); rc |= dev_upload(h, &py, f.y);
+            F.t = pt; F.y = py;
+        }
+        (w == 0 ? d.top : d.bot) = F;
+    }
+    d.maxdelta = h->cfg.maxdelta; d.courant = h->cfg.courant; d.dtmin = h->cfg.dtmin; d.dtmax = h->cfg.dtmax;
+    d.lite_miniters = h->cfg.lite_miniters; d.lite_maxiters = h->cfg.lite_maxiters; d.lite_tol = h->cfg.lite_tol;
+    if (rc) return rc;
+    // heat+salt extras
+    rc = salt_finalize(h, zc);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->dirty = false;
+    return CGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// state
+// ------------------------------------------------------------------------------------------------
+__global__ void k_fill_state(double* t, double* dt, long long* steps, long long* iters, int* status, long long M, double t0, double dt0)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < M) { t[i] = t0; dt[i] = dt0; steps[i] = 0; iters[i] = 0; status[i] = 0; }
+}
+
+extern "C" int cgb_set_state(cgb_handle* h, const double* u, double t0)
+{
+    if (!h || !u) return CGB_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    size_t nu = (size_t)h->nvar * h->N * h->M;
+    CUDA_TRY(h, cudaMemcpyAsync(h->dev.u, u, nu * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    int thr = 256;
+    k_fill_state<<<(unsigned)((h->M + thr - 1) / thr), thr, 0, h->stream>>>(h->dev.t, h->dev.dt, h->dev.steps, h->dev.iters, h->dev.status, h->M, t0, h->cfg.dt0);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->have_state = true;
+    return CGB_OK;
+}
+
+extern "C" int cgb_synchronize(cgb_handle* h)
+{
+    if (!h) return CGB_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    return CGB_OK;
+}
+
+extern "C" int cgb_get_state(cgb_handle* h, double* u, double* t, double* dt)
+{
+    if (!h) return CGB_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    size_t nu = (size_t)h->nvar * h->N * h->M;
+    if (u) CUDA_TRY(h, cudaMemcpyAsync(u, h->dev.u, nu * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (t) CUDA_TRY(h, cudaMemcpyAsync(t, h->dev.t, h->M * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (dt) CUDA_TRY(h, cudaMemcpyAsync(dt, h->dev.dt, h->M * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return CGB_OK;
+}
+
+extern "C" int cgb_get_status(cgb_handle* h, int32_t* status, int64_t* steps)
+{
+    if (!h) return CGB_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (status) CUDA_TRY(h, cudaMemcpyAsync(status, h->dev.status, h->M * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (steps) CUDA_TRY(h, cudaMemcpyAsync(steps, h->dev.steps, h->M * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return CGB_OK;
+}
+
+extern "C" int cgb_get_stats(cgb_handle* h, cgb_stats* out)
+{
+    if (!h || !out) return CGB_ERR_INVALID;
+    size_t M = (size_t)h->M;
+    std::vector<long long> steps(M), iters(M);
+    std::vector<int> status(M);
+    std::vector<double> dt(M);
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaMemcpyAsync(steps.data(), h->dev.steps, M * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(iters.data(), h->dev.iters, M * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(status.data(), h->dev.status, M * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(dt.data(), h->dev.dt, M * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cgb_stats s{};
+    s.n_columns = h->M; s.n_cells = h->N;
+    s.min_steps = steps[0]; s.max_steps = steps[0]; s.min_dt = dt[0]; s.max_dt = dt[0];
+    for (size_t c = 0; c < M; ++c) {
+        s.column_steps += steps[c]; s.lite_iterations += iters[c]; s.status_or |= status[c];
+        s.min_steps = std::min<int64_t>(s.min_steps, steps[c]); s.max_steps = std::max<int64_t>(s.max_steps, steps[c]);
+        s.min_dt = std::min(s.min_dt, dt[c]); s.max_dt = std::max(s.max_dt, dt[c]);
+    }
+    s.cell_steps = s.column_steps * h->N;
+    s.kernel_launches = h->launches;
+    *out = s;
+    return CGB_OK;
+}
+
+extern "C" int cgb_device_state(cgb_handle* h, void** u_dev, void** t_dev, void** dt_dev)
+{
+    if (!h) return CGB_ERR_INVALID;
+    if (u_dev) *u_dev = h->dev.u;
+    if (t_dev) *t_dev = h->dev.t;
+    if (dt_dev) *dt_dev = h->dev.dt;
+    return CGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel dispatch
+// ------------------------------------------------------------------------------------------------
+static bool all_freewater(const cgb_handle* h)
+{
+    for (int l = 0; l < h->nl; ++l)
+        if (h->fc_kind[l] != CGB_FC_FREEWATER) return false;
+    return true;
+}
+
+template <int CPL, bool FAST, bool DIAG>
+static int launch_euler_t(cgb_handle* h, double t_target, const Diag& D)
+{
+    auto kern = k_heat_euler<CPL, FAST, DIAG>;
+    size_t smem = (size_t)(5 * CPL * 32 + 4 * h->nl * LC_STRIDE) * sizeof(double);
+    static int blocks_per_sm = 0;   // per instantiation
+    if (blocks_per_sm == 0) {
+        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, 128, smem));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    long long tiles = (h->M + 3) / 4;
+    long long grid = std::min<long long>(tiles, (long long)h->num_sms * blocks_per_sm);
+    CUDA_TRY(h, cudaMemsetAsync(h->dev.counter, 0, sizeof(unsigned long long), h->stream));
+    kern<<<(unsigned)grid, 128, smem, h->stream>>>(h->dev, t_target, D);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return CGB_OK;
+}
+
+template <bool FAST, bool DIAG>
+static int launch_euler_c(cgb_handle* h, double t_target, const Diag& D)
+{
+    int cpl = (h->N + 31) / 32;
+    switch (cpl) {
+    case 1: return launch_euler_t<1, FAST, DIAG>(h, t_target, D);
+    case 2: return launch_euler_t<2, FAST, DIAG>(h, t_target, D);
+    case 3: case 4: return launch_euler_t<4, FAST, DIAG>(h, t_target, D);
+    case 5: case 6: return launch_euler_t<6, FAST, DIAG>(h, t_target, D);
+    case 7: return launch_euler_t<7, FAST, DIAG>(h, t_target, D);
+    case 8: return launch_euler_t<8, FAST, DIAG>(h, t_target, D);
+    case 9: return launch_euler_t<9, FAST, DIAG>(h, t_target, D);
+    case 10: return launch_euler_t<10, FAST, DIAG>(h, t_target, D);
+    case 11: case 12: return launch_euler_t<12, FAST, DIAG>(h, t_target, D);
+    default: return launch_euler_t<16, FAST, DIAG>(h, t_target, D);
+    }
+}
+
+static int launch_advance_inner(cgb_handle* h, double t_target);
+
+static int launch_advance(cgb_handle* h, double t_target)
+{
+    if (!h->profiling) return launch_advance_inner(h, t_target);
+    cudaEvent_t a, b;
+    CUDA_TRY(h, cudaEventCreate(&a));
+    CUDA_TRY(h, cudaEventCreate(&b));
+    CUDA_TRY(h, cudaEventRecord(a, h->stream));
+    int rc = launch_advance_inner(h, t_target);
+    CUDA_TRY(h, cudaEventRecord(b, h->stream));
+    h->prof_events.emplace_back(a, b);
+    return rc;
+}
+
+static int launch_advance_inner(cgb_handle* h, double t_target)
+{
+    Diag D{};
+    if (h->cfg.physics == CGB_PHYSICS_HEAT_SALT) return salt_launch(h, t_target, false, D, nullptr);
+    if (h->cfg.stepper == CGB_STEPPER_LITE_IMPLICIT) return lite_launch(h, t_target, false, D);
+    bool fast = all_freewater(h) && h->cfg.limiter == CGB_LIMITER_MAXDELTA;
+    return fast ? launch_euler_c<true, false>(h, t_target, D) : launch_euler_c<false, false>(h, t_target, D);
+}
+
+static int launch_diag(cgb_handle* h, double t, const Diag& D)
+{
+    if (h->cfg.stepper == CGB_STEPPER_LITE_IMPLICIT) return lite_launch(h, t, true, D);
+    return launch_euler_c<false, true>(h, t, D);
+}
+
+extern "C" int cgb_advance_to(cgb_handle* h, double t_target)
+{
+    if (!h) return CGB_ERR_INVALID;
+    if (!h->have_state) CGB_FAIL(h, CGB_ERR_INVALID, "cgb_set_state has not been called");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = finalize(h);
+    if (rc) return rc;
+    return launch_advance(h, t_target);
+}
+
+// diag variables of the heat path
+static int diag_slot(cgb_handle* h, const char* var, Diag& D, double** ptr, size_t* count)
+{
+    size_t NM = (size_t)h->N * h->M, EM = (size_t)(h->N + 1) * h->M;
+    double* s = h->d_scratch;
+    *count = NM;
+    std::string v(var);
+    if (v == "T") D.T = s; else if (v == "thw") D.thw = s; else if (v == "C") D.C = s; else if (v == "dHdT") D.dHdT = s;
+    else if (v == "dthwdT") D.dthwdT = s; else if (v == "kc") D.kc = s; else if (v == "dH") D.dH = s;
+    else if (v == "k") { D.k = s; *count = EM; } else if (v == "jH") { D.jH = s; *count = EM; }
+    else if (v == "DT_an") D.an = s; else if (v == "DT_as") D.as = s; else if (v == "DT_ap") D.ap = s; else if (v == "DT_bp") D.bp = s;
+    else CGB_FAIL(h, CGB_ERR_INVALID, "unknown diagnostic '%s'", var);
+    *ptr = s;
+    return CGB_OK;
+}
+
+extern "C" int cgb_get_diag(cgb_handle* h, const char* var, double t, double* out)
+{
+    if (!h || !var || !out) return CGB_ERR_INVALID;
+    if (!h->have_state) CGB_FAIL(h, CGB_ERR_INVALID, "cgb_set_state has not been called");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = finalize(h);
+    if (rc) return rc;
+    if (h->cfg.physics == CGB_PHYSICS_HEAT_SALT) return salt_get_diag(h, var, t, out);
+    Diag D{};
+    double* p; size_t cnt;
+    rc = diag_slot(h, var, D, &p, &cnt);
+    if (rc) return rc;
+    rc = launch_diag(h, t, D);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(out, p, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return CGB_OK;
+}
+
+extern "C" int cgb_rhs(cgb_handle* h, double t, double* du_out)
+{
+    if (!h || !du_out) return CGB_ERR_INVALID;
+    if (h->cfg.physics == CGB_PHYSICS_HEAT_SALT) {
+        int rc = cgb_get_diag(h, "dT", t, du_out);
+        if (rc) return rc;
+        return cgb_get_diag(h, "dc", t, du_out + (size_t)h->N * h->M);
+    }
+    if (h->cfg.stepper == CGB_STEPPER_LITE_IMPLICIT) {   // heat_implicit.jl:106: du == 0
+        std::memset(du_out, 0, sizeof(double) * (size_t)h->N * h->M);
+        return CGB_OK;
+    }
+    return cgb_get_diag(h, "dH", t, du_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// solve(prob; saveat): advance + save, D2H overlapped on a second stream
+// ------------------------------------------------------------------------------------------------
+extern "C" int cgb_solve_saveat(cgb_handle* h, const double* tsave, int64_t nsave, const char* vars, double* out)
+{
+    if (!h || !tsave || !vars || !out || nsave < 1) return CGB_ERR_INVALID;
+    if (!h->have_state) CGB_FAIL(h, CGB_ERR_INVALID, "cgb_set_state has not been called");
+    if (h->cfg.physics == CGB_PHYSICS_HEAT_SALT) CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "cgb_solve_saveat: heat+salt uses cgb_advance_to + cgb_get_state");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = finalize(h);
+    if (rc) return rc;
+    std::vector<std::string> names;
+    {
+        std::string s(vars), cur;
+        for (char c : s) { if (c == ',') { if (!cur.empty()) names.push_back(cur); cur.clear(); } else if (c != ' ') cur.push_back(c); }
+        if (!cur.empty()) names.push_back(cur);
+    }
+    if (names.empty()) CGB_FAIL(h, CGB_ERR_INVALID, "no variables to save");
+    for (auto& n : names)
+        if (n != "H" && n != "T" && n != "thw") CGB_FAIL(h, CGB_ERR_INVALID, "cgb_solve_saveat can save H, T, thw (got '%s')", n.c_str());
+    size_t NM = (size_t)h->N * h->M, per_save = NM * names.size();
+    if (h->stage_elems < per_save) {
+        for (int i = 0; i < 2; ++i) {
+            if (h->d_stage[i]) cudaFree(h->d_stage[i]);
+        if (i == 0 && h->d_lite) cudaFree(h->d_lite);
+            h->d_stage[i] = nullptr;
+            cudaError_t e = cudaMalloc((void**)&h->d_stage[i], per_save * sizeof(double));
+            if (e != cudaSuccess) CGB_FAIL(h, CGB_ERR_ALLOC, "staging buffer: %s", cudaGetErrorString(e));
+        }
+        h->stage_elems = per_save;
+    }
+    for (int64_t s = 0; s < nsave; ++s) {
+        int b = (int)(s & 1);
+        rc = launch_advance(h, tsave[s]);
+        if (rc) return rc;
+        if (s >= 2) CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->stage_free[b], 0));
+        Diag D{};
+        bool need_diag = false;
+        for (size_t v = 0; v < names.size(); ++v) {
+            double* dst = h->d_stage[b] + v * NM;
+            if (names[v] == "H") CUDA_TRY(h, cudaMemcpyAsync(dst, h->dev.u, NM * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+            else if (names[v] == "T") { D.T = dst; need_diag = true; }
+            else { D.thw = dst; need_diag = true; }
+        }
+        if (need_diag) { rc = launch_diag(h, tsave[s], D); if (rc) return rc; }
+        CUDA_TRY(h, cudaEventRecord(h->stage_ready[b], h->stream));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->stage_ready[b], 0));
+        CUDA_TRY(h, cudaMemcpyAsync(out + (size_t)s * per_save, h->d_stage[b], per_save * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+        CUDA_TRY(h, cudaEventRecord(h->stage_free[b], h->copy_stream));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    return CGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ensemble partial sums: one block per cell, coalesced over columns
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ensemble_partial(const double* __restrict__ x, long long M, int N, double* __restrict__ out)
+{
+    int cell = blockIdx.x;
+    const double* row = x + (size_t)cell * M;
+    double s = 0.0, q = 0.0;
+    for (long long c = threadIdx.x; c < M; c += blockDim.x) { double v = row[c]; s += v; q = fma(v, v, q); }
+    __shared__ double ss[8], sq[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(FULL, s, o); q += __shfl_xor_sync(FULL, q, o); }
+    if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = s; sq[threadIdx.x >> 5] = q; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0;
+        for (int w = 0; w < 8; ++w) { a += ss[w]; b += sq[w]; }
+        out[cell] = a; out[N + cell] = b;
+    }
+}
+
+extern "C" int cgb_ensemble_partial_device(cgb_handle* h, const char* var, double t, void* out_dev)
+{
+    if (!h || !var || !out_dev) return CGB_ERR_INVALID;
+    if (!h->have_state) CGB_FAIL(h, CGB_ERR_INVALID, "cgb_set_state has not been called");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = finalize(h);
+    if (rc) return rc;
+    const double* src = nullptr;
+    if (std::strcmp(var, "H") == 0 && h->cfg.physics == CGB_PHYSICS_HEAT) src = h->dev.u;
+    else {
+        if (h->cfg.physics == CGB_PHYSICS_HEAT_SALT) CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "ensemble moments: heat only");
+        Diag D{}; double* p; size_t cnt;
+        rc = diag_slot(h, var, D, &p, &cnt);
+        if (rc) return rc;
+        if (cnt != (size_t)h->N * h->M) CGB_FAIL(h, CGB_ERR_INVALID, "ensemble moments need a cell variable");
+        rc = launch_diag(h, t, D);
+        if (rc) return rc;
+        src = p;
+    }
+    k_ensemble_partial<<<h->N, 256, 0, h->stream>>>(src, h->M, h->N, static_cast<double*>(out_dev));
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return CGB_OK;
+}
+
+extern "C" int cgb_ensemble_partial(cgb_handle* h, const char* var, double t, double* sum, double* sumsq)
+{
+    if (!h || !sum || !sumsq) return CGB_ERR_INVALID;
+    double* tmp = h->d_scratch + (size_t)(cgb_handle::kScratch - 1) * (h->N + 1) * h->M;   // last scratch slot
+    int rc = cgb_ensemble_partial_device(h, var, t, tmp);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpy(sum, tmp, h->N * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(h, cudaMemcpy(sumsq, tmp + h->N, h->N * sizeof(double), cudaMemcpyDeviceToHost));
+    return CGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// measurement
+// ------------------------------------------------------------------------------------------------
+extern "C" int cgb_profile_enable(cgb_handle* h, int32_t on)
+{
+    if (!h) return CGB_ERR_INVALID;
+    h->profiling = on != 0;
+    return CGB_OK;
+}
+
+extern "C" int cgb_profile_read(cgb_handle* h, int64_t* n_launches, double* total_ms)
+{
+    if (!h || !n_launches || !total_ms) return CGB_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    double tot = 0.0;
+    for (auto& pr : h->prof_events) {
+        float ms = 0.f;
+        CUDA_TRY(h, cudaEventElapsedTime(&ms, pr.first, pr.second));
+        tot += ms;
+        cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+    }
+    *n_launches = (int64_t)h->prof_events.size();
+    *total_ms = tot;
+    h->prof_events.clear();
+    return CGB_OK;
+}

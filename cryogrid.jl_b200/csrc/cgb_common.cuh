@@ -1,0 +1,186 @@
+// cgb_common.cuh -- shared device structs and math helpers for libcgb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace cgb {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// per-(column, layer) derived constants staged in shared memory (one block per warp)
+constexpr int LC_STRIDE = 20;
+enum LayerConst {
+    LC_THWI = 0,   // θwi = por*sat                        (Soils/para/simple.jl:19,87)
+    LC_LTH,        // L*θwi                                 (heat_conduction.jl:40)
+    LC_THTOT,      // max(1e-8, θwi)                        (FreezeCurves.freewater)
+    LC_INVLTHTOT,  // 1/(L*θtot)
+    LC_CB,         // heat capacity at θw = 0               (heat_methods.jl:52-57)
+    LC_KB,         // Σ sqrt(k)θ at θw = 0                  (thermal_properties.jl:37)
+    LC_POR,        // θsat
+    LC_THRES,
+    LC_ALPHA,
+    LC_N,
+    LC_M,          // 1 - 1/n
+    LC_PSI0,       // ψ(θtot)
+    LC_TSTAR,      // T* [K]
+    LC_CFAC,       // β Lsl/(g T*)
+    LC_CBS,        // sfccheatcap at θw = 0 (with the (1-θsat) quirk, soil_heat.jl:13-14)
+    LC_KIND,       // int: freeze-curve kind | solver<<8
+    LC_TABOFF,     // int: LUT offset
+    LC_TABLEN,     // int: LUT length | extrap<<24
+    LC_SAT,        // θwi/por
+    LC_SPARE
+};
+
+struct Forcing {
+    int kind;                 // 0 constant, 1 periodic, 2 table
+    int n;
+    double value;
+    double period, amplitude, phase, level;
+    const double* t;
+    const double* y;
+};
+
+// Everything a kernel needs; passed by value (__grid_constant__).
+struct Dev {
+    int N, n_layers, nvar;
+    long long M;
+    double* u;                // [nvar*N*M] column-fastest
+    double* t;                // [M]
+    double* dt;               // [M]
+    long long* steps;         // [M]
+    long long* iters;         // [M] (LiteImplicit)
+    int* status;              // [M]
+    unsigned long long* counter; // work-stealing cursor
+    // stratigraphy / parameters
+    const int* cell_layer;    // [N]
+    const int* fc_kind;       // [n_layers] kind | solver<<8
+    const double *por, *sat, *org;                               // [n_layers*M]
+    const double *vg_alpha, *vg_n, *theta_res, *Tm, *beta, *omega; // [n_layers*M]
+    const int* table_map;     // [n_layers*M] or nullptr
+    const double* lutH; const double* lutT;
+    const int* lut_off; const int* lut_len; const int* lut_extrap;
+    // thermal properties
+    double sk_w, sk_i, sk_a, sk_m, sk_o;   // sqrt(kh_*)
+    double ch_w, ch_i, ch_a, ch_m, ch_o, L;
+    double g, Lsl, R, rho_w;
+    // grid (device arrays)
+    const double* dk;         // [N]   cell thickness
+    const double* inv_dk;     // [N]
+    const double* dxc;        // [N-1] midpoint distances
+    const double* eW1;        // [N+1] weight of the upper cell (Δk[e-1]), interior edges
+    const double* eW2;        // [N+1] weight of the lower cell (Δk[e])
+    const double* eG;         // [N+1] (w1+w2)/Δxc[e-1]
+    double ctop, cbot;        // 1/(Δk[0]/2), 1/(Δk[N-1]/2)
+    // boundary conditions
+    int top_kind, bot_kind, use_nfactor, limiter;
+    Forcing top, bot;
+    const double *nf, *nt, *top_offset, *bot_value;   // [M] (bot_value may be nullptr -> forcing)
+    double maxdelta, courant, dtmin, dtmax;
+    int lite_miniters, lite_maxiters; double lite_tol;
+    int bot_layer_first;      // first cell of the bottom layer (heat_implicit.jl:83 quirk)
+};
+
+// Optional diagnostic outputs of one RHS evaluation (device pointers, any may be null)
+struct Diag {
+    double *T, *thw, *C, *dHdT, *dthwdT, *kc;   // [N*M]
+    double *k, *jH;                             // [(N+1)*M]
+    double *dH;                                 // [N*M]
+    double *an, *as, *ap, *bp;                  // [N*M]
+};
+
+// ------------------------------------------------------------------------------------------------
+// math helpers
+// ------------------------------------------------------------------------------------------------
+
+// Reciprocal from MUFU.RCP64H + two Newton steps (<= ~1 ulp for normal inputs; no slow path).
+__device__ __forceinline__ double rcp_fast(double a)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = fma(-a, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-a, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+// Gridded(Linear) evaluation: i = searchsortedlast clamped, w = (x-x_i)/(x_{i+1}-x_i), (1-w) y_i + w y_{i+1}
+__device__ __forceinline__ double lerp_table(const double* __restrict__ xk, const double* __restrict__ yk, int nk, double x)
+{
+    int lo = 0, hi = nk - 1;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(xk + mid) <= x) lo = mid; else hi = mid;
+    }
+    double x0 = __ldg(xk + lo), x1 = __ldg(xk + lo + 1);
+    double w = (x - x0) / (x1 - x0);
+    return (1.0 - w) * __ldg(yk + lo) + w * __ldg(yk + lo + 1);
+}
+
+__device__ __forceinline__ double lut_eval(const double* __restrict__ Hk, const double* __restrict__ Tk, int nk, int extrap, double H)
+{
+    if (extrap == 0) {
+        if (H <= __ldg(Hk)) return __ldg(Tk);
+        if (H >= __ldg(Hk + nk - 1)) return __ldg(Tk + nk - 1);
+    }
+    return lerp_table(Hk, Tk, nk, H);
+}
+
+// van Genuchten θ(ψ) and dθ/dψ for ψ <= 0 (2 pow); θsat for ψ > 0.
+__device__ __forceinline__ double vg_theta(double psi, double thsat, double thres, double alpha, double n, double m, double& dth)
+{
+    if (psi <= 0.0) {
+        double x = fabs(-alpha * psi);
+        double xn = pow(x, n);
+        double base = 1.0 + xn;
+        double pb = pow(base, -m);
+        double d = thsat - thres;
+        dth = (x > 0.0) ? d * m * n * alpha * (xn / x) * (pb / base) : 0.0;
+        return thres + d * pb;
+    }
+    dth = 0.0;
+    return thsat;
+}
+
+__device__ __forceinline__ double vg_psi(double th, double thsat, double thres, double alpha, double n)
+{
+    double m = 1.0 - 1.0 / n;
+    if (th < thsat) {
+        double Se = (th - thres) / (thsat - thres);
+        return -1.0 / alpha * pow(pow(Se, -1.0 / m) - 1.0, 1.0 / n);
+    }
+    return 0.0;
+}
+
+// SFCC θw(T) and dθw/dT from the staged layer constants (DallAmico / PainterKarra).
+__device__ __forceinline__ double sfcc_theta(const double* lc, double T, double& dthdT)
+{
+    double TK = T + 273.15;
+    double Tstar = lc[LC_TSTAR];
+    double psi, dpsi;
+    if (Tstar - TK >= 0.0) { psi = lc[LC_PSI0] + lc[LC_CFAC] * (TK - Tstar); dpsi = lc[LC_CFAC]; }
+    else { psi = lc[LC_PSI0]; dpsi = 0.0; }
+    double dth;
+    double thtot = lc[LC_THWI];
+    double thsat = fmax(thtot, lc[LC_POR]);
+    double thw = vg_theta(psi, thsat, lc[LC_THRES], lc[LC_ALPHA], lc[LC_N], lc[LC_M], dth);
+    dthdT = dth * dpsi;
+    return thw;
+}
+
+} // namespace cgb

@@ -1,0 +1,349 @@
+// cgb_euler.cuh -- fused diagnostic + flux + Euler + adaptive-dt kernel (explicit enthalpy heat).
+//
+// One WARP owns one column; lane l holds cells [l*CPL, (l+1)*CPL) of H in REGISTERS for the whole
+// save interval, so a column is read from HBM once per cgb_advance_to and written once, however many
+// steps it takes.  Per step a lane does, for its CPL cells (independent chains -> ILP):
+//   H -> (θw, C, T, kc)            FreeWater closed form / SFCC LUT / SFCC Newton
+//                                   (heat_conduction.jl:18-57, soil_heat.jl:116-140, thermal_properties.jl:53-66)
+//   edge conductivity + flux        harmonic mean folded into one reciprocal (math.jl:41,141)
+//   boundary fluxes                 heat_bc.jl:9-35, methods.jl:156
+//   divergence + Euler update       math.jl:68, basic_solvers.jl:66
+//   max|dH| -> next dt              butterfly shuffle; heat_conduction.jl:183-191, basic_solvers.jl:76-77,
+//                                   integrator.jl:126-131 (clip to the save time)
+// Neighbour cells across lanes travel by __shfl_up/down.  Static grid constants and the per-(column,layer)
+// soil constants live in shared memory ([slot][lane] layout: conflict-free).  Warps fetch columns from a
+// global cursor (no CTA-wide barrier in the loop), so a slow column never stalls its CTA.
+#pragma once
+#include "cgb_common.cuh"
+
+namespace cgb {
+
+// ---- per-(column,layer) constants ---------------------------------------------------------------
+__device__ __forceinline__ void layer_consts(const Dev& P, long long col, int l, double* c)
+{
+    size_t ix = (size_t)l * P.M + col;
+    double por = P.por[ix], sat = P.sat[ix], org = P.org[ix];
+    double thwi = por * sat;
+    double thm = (1.0 - por) * (1.0 - org);
+    double tho = (1.0 - por) * org;
+    double tha = 1.0 - thwi - thm - tho;
+    double thtot = fmax(1e-8, thwi);
+    c[LC_THWI] = thwi;
+    c[LC_LTH] = P.L * thwi;
+    c[LC_THTOT] = thtot;
+    c[LC_INVLTHTOT] = 1.0 / (P.L * thtot);
+    c[LC_CB] = P.ch_i * thwi + P.ch_a * tha + P.ch_m * thm + P.ch_o * tho;
+    c[LC_KB] = P.sk_i * thwi + P.sk_a * tha + P.sk_m * thm + P.sk_o * tho;
+    c[LC_POR] = por;
+    int kind = P.fc_kind[l];
+    int* ci = reinterpret_cast<int*>(c + LC_KIND);
+    ci[0] = kind; ci[1] = 0;
+    int* to = reinterpret_cast<int*>(c + LC_TABOFF);
+    int* tl = reinterpret_cast<int*>(c + LC_TABLEN);
+    to[0] = 0; to[1] = 0; tl[0] = 0; tl[1] = 0;
+    if ((kind & 0xff) != 0) {
+        double alpha = P.vg_alpha[ix], n = P.vg_n[ix], thres = P.theta_res[ix];
+        double beta = 1.0, omega = 1.0;
+        if ((kind & 0xff) == 2) { beta = P.beta[ix]; omega = P.omega[ix]; }
+        double sat_e = thwi / por;
+        double thtot_s = sat_e * por;
+        double thsat_e = fmax(thtot_s, por);
+        double psi0 = vg_psi(thtot_s, thsat_e, thres, alpha, n);
+        double TmK = P.Tm[ix] + 273.15;
+        double gT = omega * P.g / P.Lsl * psi0;
+        double Tstar = TmK + gT * TmK;
+        c[LC_THRES] = thres; c[LC_ALPHA] = alpha; c[LC_N] = n; c[LC_M] = 1.0 - 1.0 / n;
+        c[LC_PSI0] = psi0; c[LC_TSTAR] = Tstar; c[LC_CFAC] = beta * P.Lsl / (P.g * Tstar);
+        c[LC_SAT] = sat_e;
+        // sfccheatcap base (θw = 0) with the reference's (1-θsat) quirk (soil_heat.jl:13-14)
+        c[LC_CBS] = P.ch_i * thwi + P.ch_a * (por - thwi) + P.ch_m * (thm * (1.0 - por)) + P.ch_o * (tho * (1.0 - por));
+        if (((kind >> 8) & 0xff) == 0) {
+            int id = P.table_map ? P.table_map[ix] : l;
+            to[0] = P.lut_off[id];
+            tl[0] = P.lut_len[id];
+            tl[1] = P.lut_extrap[id];
+        }
+    }
+}
+
+__device__ __forceinline__ void stage_layer_consts(const Dev& P, long long col, double* lc, int lane)
+{
+    for (int l = lane; l < P.n_layers; l += 32) layer_consts(P, col, l, lc + l * LC_STRIDE);
+}
+
+// Tightly converged safeguarded Newton for T*C(θw(T)) + Lθw(T) = H (same algorithm as the oracle).
+__device__ __forceinline__ double sfcc_newton(const double* lc, double L, double dC, double H, double T0)
+{
+    double lo = -273.0, hi = 1.0e4;
+    double T = (T0 > lo && T0 < hi) ? T0 : 0.0;
+    for (int it = 0; it < 200; ++it) {
+        double dth;
+        double thw = sfcc_theta(lc, T, dth);
+        double C = fma(dC, thw, lc[LC_CBS]);
+        double r = (T * C + L * thw) - H;
+        double dHdT = C + dth * (L + T * dC);
+        if (r > 0.0) hi = T; else lo = T;
+        double Tn = T - r / dHdT;
+        if (!(Tn > lo && Tn < hi) || !isfinite(Tn)) Tn = 0.5 * (lo + hi);
+        bool done = fabs(Tn - T) <= 1e-15 * fmax(1.0, fabs(Tn));
+        T = Tn;
+        if (done) break;
+    }
+    return T;
+}
+
+// H -> (T, θw, C, dHdT, dθw/dT, kc) for one cell.
+template <bool ALL_FW>
+__device__ __forceinline__ void freezethaw_cell(const Dev& P, const double* lc, double H, double dC, double dK,
+                                                double& T, double& thw, double& C, double& dHdT, double& dth, double& kc)
+{
+    int kind = ALL_FW ? 0 : reinterpret_cast<const int*>(lc + LC_KIND)[0];
+    if (ALL_FW || (kind & 0xff) == 0) {
+        // FreeWater: heat_conduction.jl:18-57 (θw = clamp(H/Lθ,0,1) θtot; T piecewise; ∂H∂T = 1e8 at T == 0)
+        double x = H * lc[LC_INVLTHTOT];
+        double xc = fmin(fmax(x, 0.0), 1.0);
+        thw = xc * lc[LC_THTOT];
+        C = fma(dC, thw, lc[LC_CB]);
+        double invC = rcp_fast(C);
+        double Lth = lc[LC_LTH];
+        double num = (H < 0.0) ? H : ((H >= Lth) ? (H - Lth) : 0.0);
+        T = num * invC;
+        dHdT = (T == 0.0) ? 1e8 : C;
+        dth = 0.0;
+    } else {
+        // SFCC: soil_heat.jl:116-140 -- T from the presolver table (or Newton), then θw, ∂θw∂T at T.
+        int solver = (kind >> 8) & 0xff;
+        if (solver == 0) {
+            int off = reinterpret_cast<const int*>(lc + LC_TABOFF)[0];
+            const int* tl = reinterpret_cast<const int*>(lc + LC_TABLEN);
+            T = lut_eval(P.lutH + off, P.lutT + off, tl[0], tl[1], H);
+        } else {
+            T = sfcc_newton(lc, P.L, dC, H, T);
+        }
+        thw = sfcc_theta(lc, T, dth);
+        C = fma(dC, thw, lc[LC_CBS]);
+        dHdT = C + dth * (P.L + T * dC);   // heat_methods.jl:105
+    }
+    double s = fma(dK, thw, lc[LC_KB]);
+    kc = s * s;
+}
+
+// Warp-uniform forcing evaluation with a cursor into the table (t only moves forward).
+struct ForcingCursor {
+    int idx;
+    double ta, tb, ya, yb;
+};
+
+__device__ __forceinline__ void forcing_seek(const Forcing& F, ForcingCursor& c, double t)
+{
+    int lo = 0, hi = F.n - 1;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(F.t + mid) <= t) lo = mid; else hi = mid;
+    }
+    c.idx = lo;
+    c.ta = __ldg(F.t + lo); c.tb = __ldg(F.t + lo + 1);
+    c.ya = __ldg(F.y + lo); c.yb = __ldg(F.y + lo + 1);
+}
+
+__device__ __forceinline__ double forcing_eval(const Forcing& F, ForcingCursor& c, double t, int& status)
+{
+    if (F.kind == 0) return F.value;
+    if (F.kind == 1) return F.amplitude * sin(2.0 * M_PI * (t / F.period) + F.phase) + F.level;  // simple_bc.jl:37
+    if (t < __ldg(F.t) || t > __ldg(F.t + F.n - 1)) { status |= 4; return nan(""); }              // providers.jl:30-33
+    while (t >= c.tb && c.idx < F.n - 2) {
+        ++c.idx;
+        c.ta = c.tb; c.ya = c.yb;
+        c.tb = __ldg(F.t + c.idx + 1); c.yb = __ldg(F.y + c.idx + 1);
+    }
+    if (t < c.ta) forcing_seek(F, c, t);
+    double w = (t - c.ta) / (c.tb - c.ta);
+    return (1.0 - w) * c.ya + w * c.yb;
+}
+
+// -------------------------------------------------------------------------------------------------
+template <int CPL, bool FAST, bool DIAG>
+__global__ void __launch_bounds__(128) k_heat_euler(const __grid_constant__ Dev P, double t_target, Diag D)
+{
+    extern __shared__ double smem[];
+    double* sInvDk = smem;
+    double* sDk = sInvDk + CPL * 32;
+    double* sW1 = sDk + CPL * 32;
+    double* sW2 = sW1 + CPL * 32;
+    double* sG = sW2 + CPL * 32;
+    double* sLCall = sG + CPL * 32;
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int N = P.N;
+    const long long M = P.M;
+    double* lcw = sLCall + warp * (P.n_layers * LC_STRIDE);
+
+    for (int s = threadIdx.x; s < CPL * 32; s += blockDim.x) {
+        int j = s >> 5, ln = s & 31;
+        int i = ln * CPL + j;
+        bool cell = i < N, edge = (i > 0 && i < N);
+        sInvDk[s] = cell ? P.inv_dk[i] : 0.0;
+        sDk[s] = cell ? P.dk[i] : 1.0;
+        sW1[s] = edge ? P.eW1[i] : 1.0;
+        sW2[s] = edge ? P.eW2[i] : 1.0;
+        sG[s] = edge ? P.eG[i] : 0.0;
+    }
+    __syncthreads();
+
+    const double dC = P.ch_w - P.ch_i;
+    const double dK = P.sk_w - P.sk_i;
+    const int jb = (N - 1) - lane * CPL;   // local slot of the bottom cell (if in [0,CPL))
+
+    int loff[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+        int i = lane * CPL + j;
+        loff[j] = P.cell_layer[i < N ? i : N - 1] * LC_STRIDE;
+    }
+
+    for (;;) {
+        unsigned long long cu = 0;
+        if (lane == 0) cu = atomicAdd(P.counter, 1ull);
+        cu = __shfl_sync(FULL, cu, 0);
+        if (cu >= (unsigned long long)M) break;
+        const long long col = (long long)cu;
+
+        __syncwarp();
+        stage_layer_consts(P, col, lcw, lane);
+        __syncwarp();
+
+        double H[CPL], T[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            int i = lane * CPL + j;
+            H[j] = (i < N) ? P.u[(size_t)i * M + col] : 0.0;
+            T[j] = H[j] / P.ch_w;   // Newton seed (soil_heat.jl:127)
+        }
+        double t = DIAG ? t_target : P.t[col];
+        double dt = P.dt[col];
+        const double nf = P.nf[col], nt = P.nt[col], toff = P.top_offset[col];
+        int status = 0;
+        long long nsteps = 0;
+        ForcingCursor ctop, cbot;
+        if (P.top.kind == 2) forcing_seek(P.top, ctop, fmin(fmax(t, __ldg(P.top.t)), __ldg(P.top.t + P.top.n - 1)));
+        if (P.bot.kind == 2 && !P.bot_value) forcing_seek(P.bot, cbot, fmin(fmax(t, __ldg(P.bot.t)), __ldg(P.bot.t + P.bot.n - 1)));
+
+        while (DIAG || t < t_target) {
+            // ---- boundary values at the START of the step (basic_solvers.jl:61-63)
+            double vtop = forcing_eval(P.top, ctop, t, status) + toff;
+            if (P.top_kind == 0 && P.use_nfactor) vtop = ((vtop <= 0.0) ? nf : nt) * vtop;   // heat_bc.jl:78-86
+            double vbot = P.bot_value ? P.bot_value[col] : forcing_eval(P.bot, cbot, t, status);
+
+            // ---- stage A: H -> T, θw, C, kc
+            double kc[CPL], thw[CPL], C[CPL], dHdT[CPL], dth[CPL];
+#pragma unroll
+            for (int j = 0; j < CPL; ++j)
+                freezethaw_cell<FAST>(P, lcw + loff[j], H[j], dC, dK, T[j], thw[j], C[j], dHdT[j], dth[j], kc[j]);
+
+            // ---- stage B/C: edge fluxes (upper edge of every local cell)
+            double Tup = __shfl_up_sync(FULL, T[CPL - 1], 1);
+            double kup = __shfl_up_sync(FULL, kc[CPL - 1], 1);
+            double je[CPL + 1];
+            double ke[CPL];   // DIAG only
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                double T1 = (j == 0) ? Tup : T[j - 1];
+                double k1 = (j == 0) ? kup : kc[j - 1];
+                int s = j * 32 + lane;
+                double w1 = sW1[s], w2 = sW2[s];
+                double den = fma(w2, k1, w1 * kc[j]);
+                double r = rcp_fast(den);
+                double kk = k1 * kc[j];
+                je[j] = -(((T[j] - T1) * kk) * sG[s]) * r;
+                if (DIAG) ke[j] = (kk * (w1 + w2)) * r;
+            }
+            if (lane == 0) {
+                // Top: Dirichlet -k[1](T[1]-T_ub)/(Δk[1]/2)  (heat_bc.jl:9-17) ; Neumann: value (methods.jl:156)
+                je[0] = (P.top_kind == 0) ? -(kc[0] * (T[0] - vtop)) * P.ctop : vtop;
+                if (DIAG) ke[0] = kc[0];
+            }
+            je[CPL] = __shfl_down_sync(FULL, je[0], 1);
+            // ---- divergence, limiter reduction, Euler update
+            double maxabs = 0.0, mincfl = INFINITY;
+            double dH[CPL];
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                double jlow = je[j + 1];
+                if (j == jb) {
+                    // Bottom: Dirichlet -k[end](T_lb-T[end])/(Δk[end]/2) (heat_bc.jl:18-27) ; Neumann: value
+                    jlow = (P.bot_kind == 0) ? -(kc[j] * (vbot - T[j])) * P.cbot : vbot;
+                    je[j + 1] = jlow;
+                }
+                int s = j * 32 + lane;
+                dH[j] = (je[j] - jlow) * sInvDk[s];
+                maxabs = fmax(maxabs, fabs(dH[j]));
+                if (!FAST && P.limiter == 1) {
+                    double dx = sDk[s];
+                    double v = dHdT[j] * rcp_fast(kc[j]);
+                    double c = P.courant * v * (dx * dx);
+                    if (lane * CPL + j < N) mincfl = fmin(mincfl, c);
+                }
+            }
+            if (DIAG) {
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) {
+                    int i = lane * CPL + j;
+                    if (i < N) {
+                        size_t o = (size_t)i * M + col;
+                        if (D.T) D.T[o] = T[j];
+                        if (D.thw) D.thw[o] = thw[j];
+                        if (D.C) D.C[o] = C[j];
+                        if (D.dHdT) D.dHdT[o] = dHdT[j];
+                        if (D.dthwdT) D.dthwdT[o] = dth[j];
+                        if (D.kc) D.kc[o] = kc[j];
+                        if (D.dH) D.dH[o] = dH[j];
+                        if (D.k) D.k[o] = ke[j];
+                        if (D.jH) D.jH[o] = je[j];
+                        if (i == N - 1) {
+                            size_t ob = (size_t)N * M + col;
+                            if (D.k) D.k[ob] = kc[j];
+                            if (D.jH) D.jH[ob] = je[j + 1];
+                        }
+                    }
+                }
+                break;
+            }
+            maxabs = warp_max(maxabs);
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) H[j] = fma(dt, dH[j], H[j]);   // u += dt*du (basic_solvers.jl:66)
+            t = t + dt;
+            ++nsteps;
+            // ---- next dt: timestep() from the OLD du (basic_solvers.jl:76-77), then saveat! clip
+            double lim = P.maxdelta / maxabs;                             // = min_i |Δmax/dH_i| (steplimiters.jl:15-18)
+            if (!isfinite(lim)) lim = INFINITY;
+            if (!FAST && P.limiter == 1) {
+                mincfl = warp_min(mincfl);
+                lim = fmin(lim, mincfl);
+                if (!isfinite(lim)) lim = INFINITY;                      // heat_conduction.jl:180
+            } else {
+                if (!(lim > 0.0)) lim = INFINITY;                        // heat_conduction.jl:189
+            }
+            if (!(lim > 0.0)) status |= 8;                                // tile.jl:174
+            double dtn = fmax(fmin(lim, P.dtmax), P.dtmin);
+            if (t < t_target) dtn = fmin(dtn, t_target - t);             // integrator.jl:126-131
+            dt = fmin(P.dtmax, dtn);                                      // integrator.jl:89
+            if (status & 4) break;
+        }
+        if (!DIAG) {
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                int i = lane * CPL + j;
+                if (i < N) P.u[(size_t)i * M + col] = H[j];
+            }
+            if (lane == 0) {
+                P.t[col] = t;
+                P.dt[col] = dt;
+                P.steps[col] += nsteps;
+                if (status) P.status[col] |= status;
+            }
+        }
+    }
+}
+
+} // namespace cgb

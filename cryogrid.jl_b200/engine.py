@@ -1,0 +1,178 @@
+"""Engine: owns one libcgb200 handle (one GPU, one shard of columns) for a batched Tile."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+class Engine:
+    """Thin, explicit wrapper over the C ABI. All arrays crossing it are host NumPy arrays, column-fastest."""
+
+    def __init__(self, tile, stepper="euler", dt0=None, dtmin=1.0, dtmax=None, device=0,
+                 miniters=2, maxiters=1000, tolerance=1e-3, columns=None):
+        self.lib = L.load()
+        self.tile = tile
+        cols = np.arange(tile.M) if columns is None else np.asarray(columns)
+        self.columns = cols
+        M = int(cols.size)
+        N = tile.grid.ncells
+        self.N, self.M = N, M
+        lite = stepper in ("lite", "implicit", L.STEPPER_LITE_IMPLICIT)
+        if lite != bool(tile.implicit):
+            raise ValueError("LiteImplicitEuler needs HeatBalance(EnthalpyImplicit()) and CGEuler needs Diffusion1D(:H)")
+        if dt0 is None:
+            dt0 = 86400.0 if lite else 60.0          # cglite_types.jl:29 ; basic_solvers.jl:22
+        if dtmax is None:
+            dtmax = dt0 if lite else 3600.0          # cglite_types.jl:30 ; integrator.jl:55
+        lim = tile.heat.dtlim
+        is_cfl = hasattr(lim, "courant_number")
+        cfg = L.Config(
+            abi_version=L.ABI_VERSION, device=device, n_cells=N, n_layers=tile.n_layers, n_columns=M,
+            physics=L.PHYSICS_HEAT, stepper=L.STEPPER_LITE_IMPLICIT if lite else L.STEPPER_EULER,
+            limiter=L.LIMITER_CFL if is_cfl else L.LIMITER_MAXDELTA, top_kind=tile.top_kind, bot_kind=tile.bot_kind,
+            use_nfactor=tile.use_nfactor,
+            maxdelta=float(lim.maxdelta.dmax if is_cfl else lim.dmax), courant=float(lim.courant_number if is_cfl else 0.5),
+            dt0=float(dt0), dtmin=float(dtmin), dtmax=float(dtmax),
+            lite_miniters=int(miniters), lite_maxiters=int(maxiters), lite_tol=float(tolerance),
+        )
+        self.cfg = cfg
+        h = C.c_void_p()
+        rc = self.lib.cgb_create(C.byref(cfg), C.byref(h))
+        if rc != L.OK:
+            raise L.CgbError(rc, self.lib.cgb_last_error(None).decode())
+        self.h = h
+        self._push_description()
+
+    # ---- helpers
+    def _check(self, rc):
+        if rc != L.OK:
+            raise L.CgbError(rc, self.lib.cgb_last_error(self.h).decode())
+
+    def _param(self, name, arr, per):
+        a = L.as_f64(arr)
+        self._check(self.lib.cgb_set_param(self.h, name.encode(), L.dptr(a), a.size, per))
+
+    def _push_description(self):
+        t, cols = self.tile, self.columns
+        e = L.as_f64(t.grid.edges)
+        self._check(self.lib.cgb_set_grid(self.h, L.dptr(e)))
+        cl = np.ascontiguousarray(t.cell_layer, dtype=np.int32)
+        self._check(self.lib.cgb_set_layers(self.h, cl.ctypes.data_as(C.POINTER(C.c_int32))))
+        for name in ("por", "sat", "org", "vg_alpha", "vg_n", "theta_res", "Tm", "beta", "omega"):
+            self._param(name, getattr(t, name)[:, cols], L.PER_COLUMN_LAYER)
+        for k, v in t.tp.as_dict().items():
+            self._param(k, [v], L.PER_GLOBAL)
+        self._param("nf", t.nf[cols], L.PER_COLUMN)
+        self._param("nt", t.nt[cols], L.PER_COLUMN)
+        self._param("top_offset", t.top_offset[cols], L.PER_COLUMN)
+        if t.bot_value is not None:
+            self._param("bot_value", t.bot_value[cols], L.PER_COLUMN)
+        for which, f in ((L.TOP, t.top_forcing), (L.BOTTOM, t.bot_forcing)):
+            if f[0] == "table":
+                ts, ys = L.as_f64(f[1]), L.as_f64(f[2])
+                self._check(self.lib.cgb_set_forcing_table(self.h, which, L.dptr(ts), L.dptr(ys), ts.size))
+            elif f[0] == "periodic":
+                self._check(self.lib.cgb_set_forcing_periodic(self.h, which, *[float(x) for x in f[1:]]))
+            else:
+                self._check(self.lib.cgb_set_forcing_constant(self.h, which, float(f[1])))
+        any_lut = False
+        for l in range(t.n_layers):
+            self._check(self.lib.cgb_set_freezecurve(self.h, l, int(t.fc_kind[l]), int(t.fc_solver[l])))
+            any_lut |= t.fc_kind[l] != L.FC_FREEWATER and t.fc_solver[l] == L.SOLVER_LUT
+        if any_lut:
+            tabs, tmap = t.build_tables()
+            for i, (Hk, Tk, ex) in enumerate(tabs):
+                Hk, Tk = L.as_f64(Hk), L.as_f64(Tk)
+                self._check(self.lib.cgb_set_sfcc_table(self.h, i, L.dptr(Hk), L.dptr(Tk), Hk.size, ex))
+            m = np.ascontiguousarray(tmap[:, cols], dtype=np.int32)
+            self._check(self.lib.cgb_set_sfcc_table_map(self.h, m.ctypes.data_as(C.POINTER(C.c_int32))))
+
+    # ---- state
+    def set_state(self, u, t0):
+        u = L.as_f64(u)
+        if u.shape != (self.N, self.M):
+            raise ValueError(f"state must have shape {(self.N, self.M)}, got {u.shape}")
+        self._check(self.lib.cgb_set_state(self.h, L.dptr(u), float(t0)))
+
+    def get_state(self, with_time=False):
+        u = np.empty((self.N, self.M))
+        if not with_time:
+            self._check(self.lib.cgb_get_state(self.h, L.dptr(u), None, None))
+            return u
+        t = np.empty(self.M); dt = np.empty(self.M)
+        self._check(self.lib.cgb_get_state(self.h, L.dptr(u), L.dptr(t), L.dptr(dt)))
+        return u, t, dt
+
+    def status(self):
+        st = np.empty(self.M, dtype=np.int32); steps = np.empty(self.M, dtype=np.int64)
+        self._check(self.lib.cgb_get_status(self.h, st.ctypes.data_as(C.POINTER(C.c_int32)), steps.ctypes.data_as(C.POINTER(C.c_int64))))
+        return st, steps
+
+    def stats(self):
+        s = L.Stats()
+        self._check(self.lib.cgb_get_stats(self.h, C.byref(s)))
+        return {f[0]: getattr(s, f[0]) for f in L.Stats._fields_ if f[0] != "_pad"}
+
+    # ---- hot path
+    def rhs(self, t):
+        du = np.empty((self.N, self.M))
+        self._check(self.lib.cgb_rhs(self.h, float(t), L.dptr(du)))
+        return du
+
+    def advance_to(self, t_target, sync=True):
+        self._check(self.lib.cgb_advance_to(self.h, float(t_target)))
+        if sync:
+            self._check(self.lib.cgb_synchronize(self.h))
+
+    def synchronize(self):
+        self._check(self.lib.cgb_synchronize(self.h))
+
+    def diag(self, var, t):
+        n = self.N + 1 if var in ("k", "jH") else self.N
+        out = np.empty((n, self.M))
+        self._check(self.lib.cgb_get_diag(self.h, var.encode(), float(t), L.dptr(out)))
+        return out
+
+    def solve_saveat(self, tsave, savevars=("T",), out=None):
+        tsave = L.as_f64(tsave)
+        names = {"T": "T", "H": "H", "θw": "thw", "thw": "thw"}
+        vars_c = ",".join(names[v] for v in savevars)
+        shape = (tsave.size, len(savevars), self.N, self.M)
+        if out is None:
+            out = np.empty(shape)
+        assert out.shape == shape and out.flags.c_contiguous and out.dtype == np.float64
+        self._check(self.lib.cgb_solve_saveat(self.h, L.dptr(tsave), tsave.size, vars_c.encode(), L.dptr(out)))
+        return out
+
+    def ensemble_partial(self, var, t):
+        s = np.empty(self.N); q = np.empty(self.N)
+        self._check(self.lib.cgb_ensemble_partial(self.h, var.encode(), float(t), L.dptr(s), L.dptr(q)))
+        return s, q
+
+    def ensemble_partial_device(self, var, t, out_ptr):
+        self._check(self.lib.cgb_ensemble_partial_device(self.h, var.encode(), float(t), C.c_void_p(out_ptr)))
+
+    def device_pointers(self):
+        u, t, dt = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self.lib.cgb_device_state(self.h, C.byref(u), C.byref(t), C.byref(dt)))
+        return u.value, t.value, dt.value
+
+    def profile_enable(self, on=True):
+        self._check(self.lib.cgb_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        n = C.c_int64(0); ms = C.c_double(0.0)
+        self._check(self.lib.cgb_profile_read(self.h, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cgb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,107 @@
+"""GPU parity tests of the implicit (LiteImplicitEuler / CryoGridLite) path against the CPU oracle, plus the
+reference's own analytic acceptance tests (test/Solvers/cglite_implicit_tests.jl) run through the CUDA path."""
+import numpy as np
+import pytest
+
+import common
+import cryogrid_jl_b200 as cg
+
+pytestmark = pytest.mark.gpu
+
+
+def test_lite_diag_coefficients(orc):
+    tile = common.lite_ensemble_tile(ncolumns=11, seed=1234)
+    H0 = cg.initialcondition(tile)
+    eng = cg.Engine(tile, stepper="lite")
+    eng.set_state(H0, 0.0)
+    t = 40 * 86400.0
+    got = {v: eng.diag(v, t) for v in ("T", "thw", "dHdT", "kc", "k", "DT_an", "DT_as", "DT_ap", "DT_bp")}
+    for c in range(tile.M):
+        oc = orc.OracleColumn(tile, c)
+        oc.rhs(H0[:, c], t)
+        for v, name in (("T", "T"), ("thw", "thw"), ("dHdT", "dHdT"), ("kc", "kc"), ("k", "k"), ("DT_an", "an"), ("DT_as", "as"),
+                        ("DT_ap", "ap"), ("DT_bp", "bp")):
+            ref = oc.work.get(name)
+            np.testing.assert_allclose(got[v][:, c], ref, rtol=1e-12, atol=1e-12 * max(1.0, np.max(np.abs(ref))), err_msg=v)
+    assert np.all(eng.rhs(t) == 0.0)     # heat_implicit.jl:106
+    eng.close()
+
+
+def test_lite_one_year_ensemble(orc):
+    # cfg3 shape at test size: daily steps for one year; <= 1e-6 K and <= 1e-8 θw against the oracle, equal iteration counts
+    tile = common.lite_ensemble_tile(ncolumns=9, seed=1234)
+    H0 = cg.initialcondition(tile)
+    eng = cg.Engine(tile, stepper="lite")
+    eng.set_state(H0, 0.0)
+    days = [1, 2, 30, 120, 200, 365]
+    ref = {c: (H0[:, c].copy(), 0.0, 86400.0, 0, 0) for c in range(tile.M)}
+    for d in days:
+        tt = d * 86400.0
+        eng.advance_to(tt)
+        H, t, dt = eng.get_state(with_time=True)
+        st, steps = eng.status()
+        assert not st.any()
+        Tg, thwg = eng.diag("T", tt), eng.diag("thw", tt)
+        for c in range(tile.M):
+            oc = orc.OracleColumn(tile, c)
+            Hr, tr, dtr, ns, it = ref[c]
+            Hr, tr, dtr, n2, i2, s2 = oc.lite_advance(Hr, tr, dtr, tt)
+            ref[c] = (Hr, tr, dtr, ns + n2, it + i2)
+            assert s2 == 0 and t[c] == tr == tt and steps[c] == ns + n2 == d
+            oc.rhs(Hr, tt)
+            assert np.max(np.abs(Tg[:, c] - oc.work.get("T"))) <= 1e-6
+            assert np.max(np.abs(thwg[:, c] - oc.work.get("thw"))) <= 1e-8
+    total_iters = sum(v[4] for v in ref.values())
+    assert eng.stats()["lite_iterations"] == total_iters
+    eng.close()
+
+
+def test_lite_periodic_analytic_on_gpu():
+    # test/Solvers/cglite_implicit_tests.jl:14-46 through the CUDA path
+    P, A, T0 = common.YEAR, 1.0, 1.0
+    heat = cg.HeatBalance(op="implicit")
+    soil = cg.Ground(cg.SimpleSoil(por=0.0, org=0.0), heat=heat)
+    strat = cg.Stratigraphy((0.0, cg.Top(cg.PeriodicBC(cg.Dirichlet, P, 1.0, 0.0, T0))), [(0.0, soil)],
+                            (1000.0, cg.Bottom(cg.ConstantBC(cg.Neumann, 0.0))))
+    tile = cg.Tile(strat, cg.DefaultGrid_2cm, None, ncolumns=2)
+    alpha = heat.prop.kh_m / heat.prop.ch_m
+    Tan = lambda z, t: T0 + A * np.exp(-z * np.sqrt(np.pi / (alpha * P))) * np.sin(2 * np.pi * t / P - z * np.sqrt(np.pi / (alpha * P)))
+    z = tile.grid.cells
+    H0 = tile.enthalpy_from_T(np.repeat(Tan(z, 0.0)[:, None], 2, axis=1))
+    prob = cg.CryoGridProblem(tile, H0, (0.0, 5 * P), saveat=86400.0, savevars=("T",))
+    sol = cg.solve(prob, cg.LiteImplicitEuler(), dt=86400.0)
+    out = cg.CryoGridOutput(sol)
+    top10 = z <= 10.0
+    err = out.T[:, top10, 0] - Tan(z[top10][None, :], sol.t[:, None])
+    assert sol.retcode == "Success" and out.T.shape[0] == 5 * 365 + 1
+    assert np.max(np.abs(err)) < 0.01
+
+
+def test_lite_stefan_on_gpu():
+    # test/Solvers/cglite_implicit_tests.jl:49-88 through the CUDA path (thaw depth vs Neumann solution < 0.01 m)
+    from test_oracle_golden import _stefan_lambda
+    heat = cg.HeatBalance(op="implicit")
+    soil = cg.Ground(cg.SimpleSoil(por=0.3, sat=1.0, org=0.0), heat=heat)
+    strat = cg.Stratigraphy((0.0, cg.Top(cg.ConstantTemperature(1.0))), [(0.0, soil)], (1000.0, cg.Bottom(cg.ConstantBC(cg.Neumann, 0.0))))
+    tile = cg.Tile(strat, cg.DefaultGrid_2cm, None, cg.initializer("T", -1.0), ncolumns=1)
+    H0 = cg.initialcondition(tile)
+    prob = cg.CryoGridProblem(tile, H0, (0.0, 5 * common.YEAR), saveat=86400.0, savevars=("T", "θw"))
+    sol = cg.solve(prob, cg.LiteImplicitEuler(), dt=86400.0)
+    out = cg.CryoGridOutput(sol)
+    tp = heat.prop
+    k_s = (np.sqrt(tp.kh_i) * 0.3 + np.sqrt(tp.kh_m) * 0.7) ** 2
+    k_l = (np.sqrt(tp.kh_w) * 0.3 + np.sqrt(tp.kh_m) * 0.7) ** 2
+    lam, a_l = _stefan_lambda(k_s, k_l, tp.ch_i * 0.3 + tp.ch_m * 0.7, tp.ch_w * 0.3 + tp.ch_m * 0.7, -1.0, 1.0, 0.3)
+    td = np.sum(out.vars["θw"][:, :, 0] / 0.3 * tile.grid.dedges[None, :], axis=1)
+    assert np.max(np.abs(td - 2 * lam * np.sqrt(a_l * sol.t))) < 0.01
+
+
+def test_lite_maxiters_status():
+    tile = common.lite_ensemble_tile(ncolumns=4, seed=7)
+    H0 = cg.initialcondition(tile)
+    eng = cg.Engine(tile, stepper="lite", maxiters=1, tolerance=1e-12, miniters=1)
+    eng.set_state(H0, 0.0)
+    eng.advance_to(30 * 86400.0)
+    st, steps = eng.status()
+    assert np.all(st & 1) and np.all(steps == 30)     # ReturnCode.MaxIters, cglite_step.jl:74-77
+    eng.close()
