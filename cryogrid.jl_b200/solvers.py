@@ -37,7 +37,7 @@ class CryoGridSolution:
             prob, t, u, saved, stats, status, steps, retcode
 
 
-def solve(prob, alg=None, dt=None, dtmax=None, dtmin=1.0, device=0, engine=None):
+def solve(prob, alg=None, dt=None, dtmax=None, dtmin=1.0, device=0, engine=None, out=None):
     """solve(prob, alg; dt, dtmax, dtmin).  Saved variables come back as [nsave, nvars, N, M]."""
     alg = alg or CGEuler()
     lite = isinstance(alg, LiteImplicitEuler)
@@ -47,7 +47,10 @@ def solve(prob, alg=None, dt=None, dtmax=None, dtmin=1.0, device=0, engine=None)
     eng.set_state(prob.u0, t0)
     saves = prob.saveat[prob.saveat >= t0]
     savevars = prob.savevars or ("H",)
-    out = np.empty((saves.size, len(savevars), eng.N, eng.M))
+    shape = (saves.size, len(savevars), eng.N, eng.M)
+    if out is None:
+        out = np.empty(shape)          # pass a pinned buffer for full-speed D2H
+    assert out.shape == shape
     first = 0
     if saves.size and saves[0] == t0:           # initial save: basic_solvers.jl:33-37
         for v, name in enumerate(savevars):
