@@ -2,6 +2,7 @@
 // There is no CPU path here: without a CUDA device cgb_create fails with CGB_ERR_NO_DEVICE.
 #include "cgb_handle.h"
 #include "cgb_euler.cuh"
+#include "cgb_euler_fast.cuh"
 #include "cgb_lite.cuh"
 #include "cgb_salt.cuh"
 
@@ -84,6 +85,7 @@ extern "C" int cgb_create(const cgb_config* cfg, cgb_handle** out)
 extern "C" void cgb_destroy(cgb_handle* h)
 {
     if (!h) return;
+    clear_stale_error("cgb_destroy(entry)");
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
     for (void* p : h->allocs) cudaFree(p);
@@ -95,6 +97,7 @@ extern "C" void cgb_destroy(cgb_handle* h)
     }
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    clear_stale_error("cgb_destroy(exit)");
     delete h;
 }
 
@@ -302,6 +305,13 @@ static int finalize(cgb_handle* h)
         rc |= dev_upload(h, &p, v); *dst = p;
     };
     up_cl("por", &d.por); up_cl("sat", &d.sat); up_cl("org", &d.org);
+    {   // the fast FreeWater kernel needs θwi >= 1e-8 everywhere (FreezeCurves.freewater floors θtot there) and a
+        // bottom boundary value that is constant in time
+        std::vector<double> por = expand(h, h->params["por"], CGB_PER_COLUMN_LAYER), sat = expand(h, h->params["sat"], CGB_PER_COLUMN_LAYER);
+        bool ok = true;
+        for (size_t i = 0; i < por.size() && ok; ++i) ok = (por[i] * sat[i] >= 1e-8);
+        h->fast_ok = ok && (h->params.count("bot_value") || h->forc[1].kind == 0);
+    }
     up_cl("vg_alpha", &d.vg_alpha); up_cl("vg_n", &d.vg_n); up_cl("theta_res", &d.theta_res);
     up_cl("Tm", &d.Tm); up_cl("beta", &d.beta); up_cl("omega", &d.omega);
     up_c("nf", &d.nf); up_c("nt", &d.nt); up_c("top_offset", &d.top_offset);
@@ -349,6 +359,7 @@ __global__ void k_fill_state(double* t, double* dt, long long* steps, long long*
 
 extern "C" int cgb_set_state(cgb_handle* h, const double* u, double t0)
 {
+    clear_stale_error("cgb_set_state");
     if (!h || !u) return CGB_ERR_INVALID;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     size_t nu = (size_t)h->nvar * h->N * h->M;
@@ -364,6 +375,7 @@ extern "C" int cgb_set_state(cgb_handle* h, const double* u, double t0)
 
 extern "C" int cgb_synchronize(cgb_handle* h)
 {
+    clear_stale_error("cgb_synchronize");
     if (!h) return CGB_ERR_INVALID;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -373,6 +385,7 @@ extern "C" int cgb_synchronize(cgb_handle* h)
 
 extern "C" int cgb_get_state(cgb_handle* h, double* u, double* t, double* dt)
 {
+    clear_stale_error("cgb_get_state");
     if (!h) return CGB_ERR_INVALID;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     size_t nu = (size_t)h->nvar * h->N * h->M;
@@ -395,6 +408,7 @@ extern "C" int cgb_get_status(cgb_handle* h, int32_t* status, int64_t* steps)
 
 extern "C" int cgb_get_stats(cgb_handle* h, cgb_stats* out)
 {
+    clear_stale_error("cgb_get_stats");
     if (!h || !out) return CGB_ERR_INVALID;
     size_t M = (size_t)h->M;
     std::vector<long long> steps(M), iters(M);
@@ -492,13 +506,67 @@ static int launch_advance(cgb_handle* h, double t_target)
     return rc;
 }
 
+template <int CPL, int MINB>
+static int launch_fast_tb(cgb_handle* h, double t_target)
+{
+    auto kern = k_heat_euler_fast<CPL, MINB>;
+    size_t smem = (size_t)(4 * h->nl * FC_STRIDE) * sizeof(double);
+    static int blocks_per_sm = 0;   // per instantiation
+    if (blocks_per_sm == 0) {
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, 128, smem));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    long long tiles = (h->M + 3) / 4;
+    long long grid = std::min<long long>(tiles, (long long)h->num_sms * blocks_per_sm);
+    CUDA_TRY(h, cudaMemsetAsync(h->dev.counter, 0, sizeof(unsigned long long), h->stream));
+    kern<<<(unsigned)grid, 128, smem, h->stream>>>(h->dev, t_target);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return CGB_OK;
+}
+
+// Register budget of the fast kernel: MINB resident CTAs (x4 warps) per SM.  Tuned on B200 (profiles/): see DESIGN.md.
+static int fast_minb()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("CGB_FAST_MINB"); v = e ? atoi(e) : 3; if (v < 2 || v > 4) v = 3; }
+    return v;
+}
+
+template <int CPL>
+static int launch_fast_t(cgb_handle* h, double t_target)
+{
+    switch (fast_minb()) {
+    case 2: return launch_fast_tb<CPL, 2>(h, t_target);
+    case 4: return launch_fast_tb<CPL, 4>(h, t_target);
+    default: return launch_fast_tb<CPL, 3>(h, t_target);
+    }
+}
+
+static int launch_fast(cgb_handle* h, double t_target)
+{
+    int cpl = (h->N + 31) / 32;
+    switch (cpl) {
+    case 1: return launch_fast_t<1>(h, t_target);
+    case 2: return launch_fast_t<2>(h, t_target);
+    case 3: case 4: return launch_fast_t<4>(h, t_target);
+    case 5: case 6: return launch_fast_t<6>(h, t_target);
+    case 7: return launch_fast_t<7>(h, t_target);
+    case 8: return launch_fast_t<8>(h, t_target);
+    case 9: return launch_fast_t<9>(h, t_target);
+    case 10: return launch_fast_t<10>(h, t_target);
+    case 11: case 12: return launch_fast_t<12>(h, t_target);
+    default: return launch_fast_t<16>(h, t_target);
+    }
+}
+
 static int launch_advance_inner(cgb_handle* h, double t_target)
 {
     Diag D{};
     if (h->cfg.physics == CGB_PHYSICS_HEAT_SALT) return salt_launch(h, t_target, false, D, nullptr);
     if (h->cfg.stepper == CGB_STEPPER_LITE_IMPLICIT) return lite_launch(h, t_target, false, D);
-    bool fast = all_freewater(h) && h->cfg.limiter == CGB_LIMITER_MAXDELTA;
-    return fast ? launch_euler_c<true, false>(h, t_target, D) : launch_euler_c<false, false>(h, t_target, D);
+    bool fast = all_freewater(h) && h->cfg.limiter == CGB_LIMITER_MAXDELTA && h->fast_ok;
+    return fast ? launch_fast(h, t_target) : launch_euler_c<false, false>(h, t_target, D);
 }
 
 static int launch_diag(cgb_handle* h, double t, const Diag& D)
@@ -509,6 +577,7 @@ static int launch_diag(cgb_handle* h, double t, const Diag& D)
 
 extern "C" int cgb_advance_to(cgb_handle* h, double t_target)
 {
+    clear_stale_error("cgb_advance_to");
     if (!h) return CGB_ERR_INVALID;
     if (!h->have_state) CGB_FAIL(h, CGB_ERR_INVALID, "cgb_set_state has not been called");
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
@@ -535,6 +604,7 @@ static int diag_slot(cgb_handle* h, const char* var, Diag& D, double** ptr, size
 
 extern "C" int cgb_get_diag(cgb_handle* h, const char* var, double t, double* out)
 {
+    clear_stale_error("cgb_get_diag");
     if (!h || !var || !out) return CGB_ERR_INVALID;
     if (!h->have_state) CGB_FAIL(h, CGB_ERR_INVALID, "cgb_set_state has not been called");
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
@@ -572,6 +642,7 @@ extern "C" int cgb_rhs(cgb_handle* h, double t, double* du_out)
 // ------------------------------------------------------------------------------------------------
 extern "C" int cgb_solve_saveat(cgb_handle* h, const double* tsave, int64_t nsave, const char* vars, double* out)
 {
+    clear_stale_error("cgb_solve_saveat");
     if (!h || !tsave || !vars || !out || nsave < 1) return CGB_ERR_INVALID;
     if (!h->have_state) CGB_FAIL(h, CGB_ERR_INVALID, "cgb_set_state has not been called");
     if (h->cfg.physics == CGB_PHYSICS_HEAT_SALT) CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "cgb_solve_saveat: heat+salt uses cgb_advance_to + cgb_get_state");
@@ -645,6 +716,7 @@ __global__ void __launch_bounds__(256) k_ensemble_partial(const double* __restri
 
 extern "C" int cgb_ensemble_partial_device(cgb_handle* h, const char* var, double t, void* out_dev)
 {
+    clear_stale_error("cgb_ensemble_partial_device");
     if (!h || !var || !out_dev) return CGB_ERR_INVALID;
     if (!h->have_state) CGB_FAIL(h, CGB_ERR_INVALID, "cgb_set_state has not been called");
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));

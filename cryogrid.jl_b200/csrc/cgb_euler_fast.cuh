@@ -1,0 +1,204 @@
+// cgb_euler_fast.cuh -- the FreeWater + MaxDelta fast path of the fused CGEuler kernel (BASELINE cfg2).
+//
+// Same algorithm and data layout as k_heat_euler (cgb_euler.cuh): one warp per column, CPL cells per lane held in
+// registers for the whole save interval.  What differs is the arithmetic budget -- the kernel is bound by the FP64
+// pipe (64 lanes/clk/SM), so everything here minimises FP64-pipe instructions per cell-step:
+//   * one clamp serves both θw and the enthalpy inverse:  hc = clamp(H, 0, Lθ);  x = hc/Lθ;  T = (H - hc)/C
+//     (== heat_conduction.jl:18-57 whenever θwi >= 1e-8, which the launcher checks on the host)
+//   * C and sqrt-sum conductivity are single FMAs in x; 1/C and the edge denominator use MUFU.RCP64H + 2 Newton steps
+//   * harmonic mean + flux share one reciprocal:  j = -(T2-T1) k1 k2 G / (Δ2 k1 + Δ1 k2)        (math.jl:41,141)
+//   * static grid constants (Δk, 1/Δk, G) live in registers; per-layer soil constants are broadcast LDS
+//   * max|dH| over the warp is reduced on the integer REDUX unit (two 32-bit reduce-max), not on the FP64 pipe
+//   * next dt = Δmax * rcp(max|dH|); forcing interpolation multiplies by a cached 1/(t_{k+1}-t_k)
+// ~26 FP64 instructions per cell-step + ~3 amortised per-step instructions.
+#pragma once
+#include "cgb_euler.cuh"
+
+namespace cgb {
+
+constexpr int FC_STRIDE = 8;   // fast-path per-(column,layer) constants
+enum FastConst { FC_LTH = 0, FC_INVLTH, FC_CB, FC_KB, FC_DCTH, FC_DKTH };
+
+__device__ __forceinline__ double warp_max_nonneg(double v)
+{
+    // v >= 0 (or NaN-free by construction: fmax drops NaN): order of doubles == order of their bit patterns
+    unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    unsigned mhi = __reduce_max_sync(FULL, hi);
+    unsigned mlo = __reduce_max_sync(FULL, hi == mhi ? lo : 0u);
+    return __hiloint2double((int)mhi, (int)mlo);
+}
+
+template <int CPL, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_heat_euler_fast(const __grid_constant__ Dev P, double t_target)
+{
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int N = P.N;
+    const long long M = P.M;
+    double* lcw = smem + warp * (P.n_layers * FC_STRIDE);
+
+    const double dC = P.ch_w - P.ch_i;
+    const double dK = P.sk_w - P.sk_i;
+    const int jb = (N - 1) - lane * CPL;   // local slot of the bottom cell (if in [0,CPL))
+
+    // static per-cell grid constants in registers
+    double dk[CPL], idk[CPL], G[CPL], dk_up;
+    int loff[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+        int i = lane * CPL + j;
+        bool cell = i < N, edge = (i > 0 && i < N);
+        dk[j] = cell ? P.dk[i] : 1.0;
+        idk[j] = cell ? P.inv_dk[i] : 0.0;
+        G[j] = edge ? P.eG[i] : 0.0;
+        loff[j] = P.cell_layer[cell ? i : N - 1] * FC_STRIDE;
+    }
+    {
+        int i = lane * CPL - 1;
+        dk_up = (i >= 0 && i < N) ? P.dk[i] : 1.0;
+    }
+    const bool top_dirichlet = P.top_kind == 0, bot_dirichlet = P.bot_kind == 0, use_nf = P.use_nfactor != 0;
+    const int fkind = P.top.kind;
+    const int fn = P.top.n;
+    const double* __restrict__ ft = P.top.t;
+    const double* __restrict__ fy = P.top.y;
+    const double ft_first = (fkind == 2) ? __ldg(ft) : 0.0, ft_last = (fkind == 2) ? __ldg(ft + fn - 1) : 0.0;
+
+    for (;;) {
+        unsigned long long cu = 0;
+        if (lane == 0) cu = atomicAdd(P.counter, 1ull);
+        cu = __shfl_sync(FULL, cu, 0);
+        if (cu >= (unsigned long long)M) break;
+        const long long col = (long long)cu;
+
+        __syncwarp();
+        for (int l = lane; l < P.n_layers; l += 32) {
+            size_t ix = (size_t)l * M + col;
+            double por = P.por[ix], sat = P.sat[ix], org = P.org[ix];
+            double thwi = por * sat;
+            double thm = (1.0 - por) * (1.0 - org), tho = (1.0 - por) * org;
+            double tha = 1.0 - thwi - thm - tho;
+            double* c = lcw + l * FC_STRIDE;
+            double Lth = P.L * thwi;                     // θwi >= 1e-8 guaranteed by the launcher
+            c[FC_LTH] = Lth;
+            c[FC_INVLTH] = 1.0 / Lth;
+            c[FC_CB] = P.ch_i * thwi + P.ch_a * tha + P.ch_m * thm + P.ch_o * tho;
+            c[FC_KB] = P.sk_i * thwi + P.sk_a * tha + P.sk_m * thm + P.sk_o * tho;
+            c[FC_DCTH] = dC * thwi;
+            c[FC_DKTH] = dK * thwi;
+        }
+        __syncwarp();
+
+        double H[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            int i = lane * CPL + j;
+            H[j] = (i < N) ? P.u[(size_t)i * M + col] : 0.0;
+        }
+        double t = P.t[col];
+        double dt = P.dt[col];
+        const double nf = P.nf[col], nt = P.nt[col], toff = P.top_offset[col];
+        const double vbot = P.bot_value ? P.bot_value[col] : P.bot.value;   // launcher: bottom is constant in time here
+        int status = 0;
+        long long nsteps = 0;
+        // forcing cursor (warp-uniform)
+        int fidx = 0;
+        double fta = 0.0, ftb = 0.0, fya = 0.0, fyb = 0.0, finv = 0.0;
+        if (fkind == 2) {
+            double ts = fmin(fmax(t, ft_first), ft_last);
+            int lo = 0, hi = fn - 1;
+            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (__ldg(ft + mid) <= ts) lo = mid; else hi = mid; }
+            fidx = lo; fta = __ldg(ft + lo); ftb = __ldg(ft + lo + 1); fya = __ldg(fy + lo); fyb = __ldg(fy + lo + 1);
+            finv = 1.0 / (ftb - fta);
+        }
+
+        while (t < t_target) {
+            // ---- upper boundary value at the START of the step (basic_solvers.jl:61-63)
+            double vtop;
+            if (fkind == 2) {
+                if (t < ft_first || t > ft_last) { status |= 4; break; }                 // providers.jl:30-33
+                while (t >= ftb && fidx < fn - 2) {
+                    ++fidx; fta = ftb; fya = fyb;
+                    ftb = __ldg(ft + fidx + 1); fyb = __ldg(fy + fidx + 1);
+                    finv = 1.0 / (ftb - fta);
+                }
+                double w = (t - fta) * finv;
+                vtop = fma(w, fyb, (1.0 - w) * fya);
+            } else if (fkind == 1) {
+                vtop = P.top.amplitude * sin(2.0 * M_PI * (t / P.top.period) + P.top.phase) + P.top.level;   // simple_bc.jl:37
+            } else {
+                vtop = P.top.value;
+            }
+            vtop += toff;
+            if (top_dirichlet && use_nf) vtop = ((vtop <= 0.0) ? nf : nt) * vtop;     // heat_bc.jl:78-86
+
+            // ---- stage A: H -> T, kc   (heat_conduction.jl:18-57, thermal_properties.jl:37)
+            double T[CPL], kc[CPL];
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                const double* c = lcw + loff[j];
+                double hc = fmin(fmax(H[j], 0.0), c[FC_LTH]);
+                double x = hc * c[FC_INVLTH];
+                double C = fma(c[FC_DCTH], x, c[FC_CB]);
+                double s = fma(c[FC_DKTH], x, c[FC_KB]);
+                kc[j] = s * s;
+                T[j] = (H[j] - hc) * rcp_fast(C);
+            }
+            // ---- stage B/C: edge fluxes (upper edge of every local cell)
+            double Tup = __shfl_up_sync(FULL, T[CPL - 1], 1);
+            double kup = __shfl_up_sync(FULL, kc[CPL - 1], 1);
+            double je[CPL + 1];
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                double T1 = (j == 0) ? Tup : T[j - 1];
+                double k1 = (j == 0) ? kup : kc[j - 1];
+                double w1 = (j == 0) ? dk_up : dk[j - 1];
+                double den = fma(dk[j], k1, w1 * kc[j]);
+                double q = ((T1 - T[j]) * (k1 * kc[j])) * G[j];
+                je[j] = q * rcp_fast(den);
+            }
+            if (lane == 0)   // heat_bc.jl:9-17 (Dirichlet) / methods.jl:156 (Neumann)
+                je[0] = top_dirichlet ? (kc[0] * (vtop - T[0])) * P.ctop : vtop;
+            je[CPL] = __shfl_down_sync(FULL, je[0], 1);
+            // ---- divergence, limiter reduction, Euler update
+            double maxabs = 0.0;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                double jlow = je[j + 1];
+                if (j == jb) {   // heat_bc.jl:18-27,32-35
+                    jlow = bot_dirichlet ? (kc[j] * (T[j] - vbot)) * P.cbot : vbot;
+                    je[j + 1] = jlow;
+                }
+                double dH = (je[j] - jlow) * idk[j];
+                maxabs = fmax(maxabs, fabs(dH));
+                H[j] = fma(dt, dH, H[j]);                                            // basic_solvers.jl:66
+            }
+            maxabs = warp_max_nonneg(maxabs);
+            t = t + dt;
+            ++nsteps;
+            // ---- next dt (basic_solvers.jl:76-77, heat_conduction.jl:183-191, steplimiters.jl:15-18), saveat! clip
+            double lim = (maxabs > 0.0) ? P.maxdelta * rcp_fast(maxabs) : INFINITY;
+            if (!(lim > 0.0) || !(lim < INFINITY)) {
+                lim = (maxabs > 0.0) ? P.maxdelta / maxabs : INFINITY;              // rare: exact path for extremes
+                if (!isfinite(lim) || !(lim > 0.0)) lim = INFINITY;
+            }
+            double dtn = fmax(fmin(lim, P.dtmax), P.dtmin);
+            if (t < t_target) dtn = fmin(dtn, t_target - t);                         // integrator.jl:126-131
+            dt = fmin(P.dtmax, dtn);                                                  // integrator.jl:89
+        }
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            int i = lane * CPL + j;
+            if (i < N) P.u[(size_t)i * M + col] = H[j];
+        }
+        if (lane == 0) {
+            P.t[col] = t;
+            P.dt[col] = dt;
+            P.steps[col] += nsteps;
+            if (status) P.status[col] |= status;
+        }
+    }
+}
+
+} // namespace cgb

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -39,6 +40,7 @@ struct cgb_handle {
     struct HostForcing { int kind = 0; double value = 0, period = 1, amp = 0, phase = 0, level = 0; std::vector<double> t, y; } forc[2];
     bool dirty = true;        // device copy of the description is stale
     bool have_state = false;
+    bool fast_ok = false;     // FreeWater fast kernel applicable (set by finalize)
     // device memory
     std::vector<void*> allocs;
     size_t n_state_allocs = 0;   // allocations made by cgb_create (the rest belong to the description)
@@ -68,6 +70,17 @@ struct cgb_handle {
         cudaError_t _e = (expr);                                                                    \
         if (_e != cudaSuccess) CGB_FAIL(h, CGB_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e));  \
     } while (0)
+
+// Clears (and, with CGB_DEBUG=1 in the environment, reports) an error left behind by an earlier unchecked call,
+// so that a launch check never blames the wrong call.
+static inline void clear_stale_error(const char* where)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        static const bool dbg = getenv("CGB_DEBUG") != nullptr;
+        if (dbg) fprintf(stderr, "[cgb200] stale CUDA error at %s: %s\n", where, cudaGetErrorString(e));
+    }
+}
 
 template <typename T>
 static int dev_alloc(cgb_handle* h, T** p, size_t n)
