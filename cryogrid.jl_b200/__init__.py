@@ -13,6 +13,8 @@ from .model import (FreeWater, VanGenuchten, DallAmico, PainterKarra, DallAmicoS
                     HeatBalance, EnthalpyImplicit, Ground, Top, Bottom, Stratigraphy, ThermalSteadyStateInit, initializer,
                     Tile, SoilHeatTile, initialcondition, Dirichlet, Neumann)
 from .engine import Engine
+from .salt import (SaltProperties, SaltMassBalance, SaltGradient, SedimentCompactionInitializer, compaction, SalineTile,
+                   SaltEngine)
 from .solvers import CGEuler, LiteImplicitEuler, CryoGridProblem, CryoGridSolution, CryoGridOutput, solve
 
 SamoylovDefault_tempprofile = TemperatureProfile(   # models.jl:35-44

@@ -82,6 +82,16 @@ struct Dev {
     int bot_layer_first;      // first cell of the bottom layer (heat_implicit.jl:83 quirk)
 };
 
+// heat+salt extras (Physics/Salt)
+struct SaltDev {
+    const double* por_cell;   // [N] porosity profile (SedimentCompactionInitializer), shared by all columns
+    const double* benthic;    // [M] SaltGradient.benthicSalt
+    double sat, org, para_por;
+    double alpha, n, theta_res, Tm;
+    double tau, ds0, dc_max, courant, heat_courant;
+    int surface_state;
+};
+
 // Optional diagnostic outputs of one RHS evaluation (device pointers, any may be null)
 struct Diag {
     double *T, *thw, *C, *dHdT, *dthwdT, *kc;   // [N*M]

@@ -45,6 +45,7 @@ struct cgb_handle {
     std::vector<void*> allocs;
     size_t n_state_allocs = 0;   // allocations made by cgb_create (the rest belong to the description)
     cgb::Dev dev{};
+    cgb::SaltDev salt{};
     double* d_scratch = nullptr;      // diag scratch, (N+1)*M doubles x kScratch
     static constexpr int kScratch = 4;
     double* d_lite = nullptr;         // LiteImplicit scratch: 5*N*M doubles

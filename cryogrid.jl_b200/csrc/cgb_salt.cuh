@@ -1,6 +1,311 @@
-// cgb_salt.cuh -- heat+salt kernels (placeholder until implemented)
+// cgb_salt.cuh -- coupled heat + salt diffusion (SalineGround, HeatBalance(:T) + SaltMassBalance), CGEuler.
+//
+// Reference: Physics/Salt/salt_diffusion.jl:3-30 (freezethaw! with DallAmicoSalt, 2-D duals -> analytic partials
+// here), :51-78 (conductivity / diffusivity harmonic means), salt_bc.jl:18-31 + heat_bc.jl:9-35 (boundaries),
+// :124-165 (nonlineardiffusion! for dH and dc_F, per-cell 2x2 solve), :107-122 + heat_conduction.jl:162-182
+// (salt CFL + MaxDelta(5e-3), heat CFL).  Same execution model as the heat kernel: one warp per column, T and c
+// of CPL cells per lane in registers across all steps of a save interval, neighbours by shuffle, dt by warp reduction.
 #pragma once
 #include "cgb_handle.h"
-static int salt_finalize(cgb_handle*, const std::vector<double>&) { return CGB_OK; }
-static int salt_launch(cgb_handle* h, double, bool, const cgb::Diag&, void*) { CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "heat+salt not built yet"); }
-static int salt_get_diag(cgb_handle* h, const char*, double, double*) { CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "heat+salt not built yet"); }
+#include "cgb_euler.cuh"
+
+namespace cgb {
+
+struct SaltDiag {
+    double *thw, *dthwdT, *dthwdc, *C, *dHdT, *H, *kc;   // [N*M]
+    double *k, *ds, *jH, *jc;                            // [(N+1)*M]
+    double *dH, *dcF, *dT, *dc;                          // [N*M]
+};
+
+template <int CPL, bool DIAG>
+__global__ void __launch_bounds__(128) k_salt_euler(const __grid_constant__ Dev P, const __grid_constant__ SaltDev S, double t_target, SaltDiag D)
+{
+    extern __shared__ double smem[];
+    double* sInvDk = smem;
+    double* sDk = sInvDk + CPL * 32;
+    double* sW1 = sDk + CPL * 32;
+    double* sW2 = sW1 + CPL * 32;
+    double* sG = sW2 + CPL * 32;
+    const int lane = threadIdx.x & 31;
+    const int N = P.N;
+    const long long M = P.M;
+    for (int s = threadIdx.x; s < CPL * 32; s += blockDim.x) {
+        int j = s >> 5, ln = s & 31;
+        int i = ln * CPL + j;
+        bool cell = i < N, edge = (i > 0 && i < N);
+        sInvDk[s] = cell ? P.inv_dk[i] : 0.0;
+        sDk[s] = cell ? P.dk[i] : 1.0;
+        sW1[s] = edge ? P.eW1[i] : 1.0;
+        sW2[s] = edge ? P.eW2[i] : 1.0;
+        sG[s] = edge ? P.eG[i] : 0.0;
+    }
+    __syncthreads();
+    const int jb = (N - 1) - lane * CPL;
+    const double m = 1.0 - 1.0 / S.n;
+    const double TmK0 = S.Tm + 273.15;
+    const double Lf = P.Lsl * P.rho_w;
+    const double dTm_dc = TmK0 / Lf * (-P.R * TmK0);
+    // static per-cell constants (porosity profile is shared by all columns)
+    double por[CPL], psi0[CPL], thwi[CPL], Cb[CPL], Kb[CPL];
+    {
+        double thm = (1.0 - S.para_por) * (1.0 - S.org), tho = (1.0 - S.para_por) * S.org;   // mineral()/organic() use para.por
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            int i = lane * CPL + j;
+            por[j] = S.por_cell[i < N ? i : N - 1];
+            thwi[j] = por[j] * S.sat;
+            double tha = 1.0 - thwi[j] - thm - tho;
+            psi0[j] = vg_psi(S.sat * por[j], fmax(S.sat * por[j], por[j]), S.theta_res, S.alpha, S.n);
+            Cb[j] = P.ch_i * thwi[j] + P.ch_a * tha + P.ch_m * thm + P.ch_o * tho;
+            Kb[j] = P.sk_i * thwi[j] + P.sk_a * tha + P.sk_m * thm + P.sk_o * tho;
+        }
+    }
+    const double dC = P.ch_w - P.ch_i, dK = P.sk_w - P.sk_i;
+
+    for (;;) {
+        unsigned long long cu = 0;
+        if (lane == 0) cu = atomicAdd(P.counter, 1ull);
+        cu = __shfl_sync(FULL, cu, 0);
+        if (cu >= (unsigned long long)M) break;
+        const long long col = (long long)cu;
+        double T[CPL], c[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            int i = lane * CPL + j;
+            T[j] = (i < N) ? P.u[(size_t)i * M + col] : 0.0;
+            c[j] = (i < N) ? P.u[(size_t)(N + i) * M + col] : 0.0;
+        }
+        double t = DIAG ? t_target : P.t[col];
+        double dt = P.dt[col];
+        const double benthic = S.benthic[col];
+        const double vtop = P.top.value + P.top_offset[col];
+        const double vbot = P.bot_value ? P.bot_value[col] : P.bot.value;
+        int status = 0;
+        long long nsteps = 0;
+
+        while (DIAG || t < t_target) {
+            double thw[CPL], dthT[CPL], dthc[CPL], Cc[CPL], dHdT[CPL], kc[CPL], dsm[CPL];
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                // DallAmicoSalt: freezing point depression, then Dall'Amico (FreezeCurves.jl; parity unpinned)
+                double TmK = TmK0 + TmK0 / Lf * (-P.R * c[j] * TmK0);
+                double gT = P.g / P.Lsl * psi0[j];
+                double Tstar = TmK + gT * TmK;
+                double dTstar_dc = dTm_dc * (1.0 + gT);
+                double TK = T[j] + 273.15;
+                double psi, dpsi_dT, dpsi_dc;
+                if (Tstar - TK >= 0.0) {
+                    double cfac = P.Lsl / (P.g * Tstar);
+                    psi = psi0[j] + cfac * (TK - Tstar);
+                    dpsi_dT = cfac;
+                    dpsi_dc = P.Lsl / P.g * (-TK / (Tstar * Tstar)) * dTstar_dc;
+                } else { psi = psi0[j]; dpsi_dT = 0.0; dpsi_dc = 0.0; }
+                double dth;
+                double thsat = fmax(S.sat * por[j], por[j]);
+                thw[j] = vg_theta(psi, thsat, S.theta_res, S.alpha, S.n, m, dth);
+                dthT[j] = dth * dpsi_dT;
+                dthc[j] = dth * dpsi_dc;
+                Cc[j] = fma(dC, thw[j], Cb[j]);
+                dHdT[j] = Cc[j] + P.L * dthT[j];                    // salt_diffusion.jl:26
+                dsm[j] = S.ds0 * thw[j] / S.tau;                    // salt_diffusion.jl:28
+                double s = fma(dK, thw[j], Kb[j]);
+                kc[j] = s * s;
+            }
+            double Tup = __shfl_up_sync(FULL, T[CPL - 1], 1);
+            double cup = __shfl_up_sync(FULL, c[CPL - 1], 1);
+            double kup = __shfl_up_sync(FULL, kc[CPL - 1], 1);
+            double dup = __shfl_up_sync(FULL, dsm[CPL - 1], 1);
+            double jH[CPL + 1], jc[CPL + 1], ke[CPL], de[CPL];
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                double T1 = (j == 0) ? Tup : T[j - 1], c1 = (j == 0) ? cup : c[j - 1];
+                double k1 = (j == 0) ? kup : kc[j - 1], d1 = (j == 0) ? dup : dsm[j - 1];
+                int s = j * 32 + lane;
+                double w1 = sW1[s], w2 = sW2[s], g = sG[s];
+                // harmonicmean + flux (math.jl:41,141) -- true divisions: this kernel is dominated by pow()
+                ke[j] = (w1 + w2) / (w1 * (1.0 / k1) + w2 * (1.0 / kc[j]));
+                de[j] = (w1 + w2) / (w1 * (1.0 / d1) + w2 * (1.0 / dsm[j]));
+                double idx = g / (w1 + w2);                          // 1/Δxc
+                jH[j] = -ke[j] * (T[j] - T1) * idx;
+                jc[j] = -de[j] * (c[j] - c1) * idx;
+                if (g == 0.0) { jH[j] = 0.0; jc[j] = 0.0; }
+            }
+            if (lane == 0) {
+                ke[0] = kc[0]; de[0] = dsm[0];
+                jH[0] = -kc[0] * (T[0] - vtop) * P.ctop;                                       // heat_bc.jl:9-17
+                jc[0] = (S.surface_state == 0) ? -dsm[0] * (c[0] - benthic) * P.ctop : 0.0;      // salt_bc.jl:18-31
+            }
+            jH[CPL] = __shfl_down_sync(FULL, jH[0], 1);
+            jc[CPL] = __shfl_down_sync(FULL, jc[0], 1);
+            double dTv[CPL], dcv[CPL], dHv[CPL], dcF[CPL];
+            double lim = INFINITY, limh = INFINITY;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                double jHl = jH[j + 1], jcl = jc[j + 1];
+                if (j == jb) { jHl = vbot; jcl = 0.0; jH[j + 1] = jHl; jc[j + 1] = jcl; }
+                int s = j * 32 + lane;
+                dHv[j] = (jH[j] - jHl) * sInvDk[s];
+                dcF[j] = (jc[j] - jcl) * sInvDk[s];
+                // salt_diffusion.jl:150-163
+                double A = dHdT[j], B = P.L * dthc[j], Dd = dHv[j];
+                double E = thw[j] + c[j] * dthc[j], F = c[j] * dthT[j], Gg = dcF[j];
+                double det = A * E - B * F;
+                dTv[j] = (-B * Gg + Dd * E) / det;
+                dcv[j] = (-F * Dd + A * Gg) / det;
+                if (lane * CPL + j < N) {
+                    double dx = sDk[s];
+                    double dts = S.courant * (1.0 / de[j]) * (dx * dx);                         // salt_diffusion.jl:112-119
+                    lim = fmin(fmin(lim, dts), S.dc_max / fabs(dcv[j]));
+                    double dth = S.heat_courant * (dHdT[j] / kc[j]) * (dx * dx);                // heat_conduction.jl:170-178
+                    limh = fmin(limh, dth);
+                }
+            }
+            if (DIAG) {
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) {
+                    int i = lane * CPL + j;
+                    if (i < N) {
+                        size_t o = (size_t)i * M + col;
+                        if (D.thw) D.thw[o] = thw[j];
+                        if (D.dthwdT) D.dthwdT[o] = dthT[j];
+                        if (D.dthwdc) D.dthwdc[o] = dthc[j];
+                        if (D.C) D.C[o] = Cc[j];
+                        if (D.dHdT) D.dHdT[o] = dHdT[j];
+                        if (D.H) D.H[o] = T[j] * Cc[j] + P.L * thw[j];
+                        if (D.kc) D.kc[o] = kc[j];
+                        if (D.k) D.k[o] = ke[j];
+                        if (D.ds) D.ds[o] = de[j];
+                        if (D.jH) D.jH[o] = jH[j];
+                        if (D.jc) D.jc[o] = jc[j];
+                        if (D.dH) D.dH[o] = dHv[j];
+                        if (D.dcF) D.dcF[o] = dcF[j];
+                        if (D.dT) D.dT[o] = dTv[j];
+                        if (D.dc) D.dc[o] = dcv[j];
+                        if (i == N - 1) {
+                            size_t ob = (size_t)N * M + col;
+                            if (D.k) D.k[ob] = kc[j];
+                            if (D.ds) D.ds[ob] = dsm[j];
+                            if (D.jH) D.jH[ob] = jH[j + 1];
+                            if (D.jc) D.jc[ob] = jc[j + 1];
+                        }
+                    }
+                }
+                break;
+            }
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) { T[j] = fma(dt, dTv[j], T[j]); c[j] = fma(dt, dcv[j], c[j]); }
+            t = t + dt;
+            ++nsteps;
+            lim = warp_min(lim);
+            limh = warp_min(limh);
+            if (!isfinite(limh)) limh = INFINITY;
+            lim = fmin(lim, limh);
+            if (!(lim > 0.0)) status |= 8;
+            double dtn = fmax(fmin(lim, P.dtmax), P.dtmin);
+            if (t < t_target) dtn = fmin(dtn, t_target - t);
+            dt = fmin(P.dtmax, dtn);
+        }
+        if (!DIAG) {
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                int i = lane * CPL + j;
+                if (i < N) { P.u[(size_t)i * M + col] = T[j]; P.u[(size_t)(N + i) * M + col] = c[j]; }
+            }
+            if (lane == 0) {
+                P.t[col] = t; P.dt[col] = dt; P.steps[col] += nsteps;
+                if (status) P.status[col] |= status;
+            }
+        }
+    }
+}
+
+} // namespace cgb
+
+// ---- host side -------------------------------------------------------------------------------------
+static int salt_finalize(cgb_handle* h, const std::vector<double>&)
+{
+    using namespace cgb;
+    if (h->cfg.physics != CGB_PHYSICS_HEAT_SALT) return CGB_OK;
+    if (h->cfg.stepper != CGB_STEPPER_EULER) CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "heat+salt supports CGEuler only (as the reference)");
+    SaltDev& s = h->salt;
+    ParamArray& por = h->params["por"];
+    std::vector<double> pc(h->N);
+    for (int i = 0; i < h->N; ++i) pc[i] = (por.per == CGB_PER_CELL) ? por.v[i] : por.v[0];
+    double* p_por; int rc = dev_upload(h, &p_por, pc); if (rc) return rc;
+    s.por_cell = p_por;
+    ParamArray& b = h->params["benthic_salt"];
+    std::vector<double> bc((size_t)h->M);
+    for (long long c = 0; c < h->M; ++c) bc[c] = (b.per == CGB_PER_COLUMN) ? b.v[c] : b.v[0];
+    double* p_b; rc = dev_upload(h, &p_b, bc); if (rc) return rc;
+    s.benthic = p_b;
+    auto G = [&](const char* n) { return h->params[n].v[0]; };
+    s.sat = G("sat"); s.org = G("org"); s.para_por = G("salt_para_por");
+    s.alpha = G("vg_alpha"); s.n = G("vg_n"); s.theta_res = G("theta_res"); s.Tm = G("Tm");
+    s.tau = G("tau"); s.ds0 = G("ds0"); s.dc_max = G("salt_dc_max");
+    s.courant = h->cfg.courant; s.heat_courant = 0.5;                 // salt_types.jl:13 ; heat_types.jl:17
+    s.surface_state = (int)G("salt_surface_state");
+    if (h->forc[0].kind != 0 || (h->forc[1].kind != 0 && !h->params.count("bot_value")))
+        CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "heat+salt supports constant boundary values (ConstantTemperature / GeothermalHeatFlux)");
+    if (h->cfg.top_kind != CGB_BC_DIRICHLET || h->cfg.bot_kind != CGB_BC_NEUMANN)
+        CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "heat+salt supports a Dirichlet top and Neumann bottom (examples/heat_sfcc_salt_constantbc.jl)");
+    return CGB_OK;
+}
+
+template <int CPL, bool DIAG>
+static int salt_launch_t(cgb_handle* h, double t_target, const cgb::SaltDiag& D)
+{
+    using namespace cgb;
+    auto kern = k_salt_euler<CPL, DIAG>;
+    size_t smem = (size_t)(5 * CPL * 32) * sizeof(double);
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, 128, smem));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    long long grid = std::min<long long>((h->M + 3) / 4, (long long)h->num_sms * blocks_per_sm);
+    CUDA_TRY(h, cudaMemsetAsync(h->dev.counter, 0, sizeof(unsigned long long), h->stream));
+    kern<<<(unsigned)grid, 128, smem, h->stream>>>(h->dev, h->salt, t_target, D);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return CGB_OK;
+}
+
+template <bool DIAG>
+static int salt_launch_c(cgb_handle* h, double t_target, const cgb::SaltDiag& D)
+{
+    int cpl = (h->N + 31) / 32;
+    if (cpl <= 2) return salt_launch_t<2, DIAG>(h, t_target, D);
+    if (cpl <= 4) return salt_launch_t<4, DIAG>(h, t_target, D);
+    if (cpl <= 6) return salt_launch_t<6, DIAG>(h, t_target, D);
+    if (cpl <= 7) return salt_launch_t<7, DIAG>(h, t_target, D);
+    if (cpl <= 9) return salt_launch_t<9, DIAG>(h, t_target, D);
+    CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "heat+salt kernels are built for n_cells <= 288");
+}
+
+static int salt_launch(cgb_handle* h, double t_target, bool diag, const cgb::Diag&, void* sd)
+{
+    cgb::SaltDiag D{};
+    if (diag) return salt_launch_c<true>(h, t_target, *static_cast<cgb::SaltDiag*>(sd));
+    return salt_launch_c<false>(h, t_target, D);
+}
+
+static int salt_get_diag(cgb_handle* h, const char* var, double t, double* out)
+{
+    using namespace cgb;
+    SaltDiag D{};
+    double* s = h->d_scratch;
+    size_t NM = (size_t)h->N * h->M, cnt = NM;
+    std::string v(var);
+    if (v == "thw") D.thw = s; else if (v == "dthwdT") D.dthwdT = s; else if (v == "dthwdc") D.dthwdc = s; else if (v == "C") D.C = s;
+    else if (v == "dHdT") D.dHdT = s; else if (v == "H") D.H = s; else if (v == "kc") D.kc = s; else if (v == "dH") D.dH = s;
+    else if (v == "dc_F") D.dcF = s; else if (v == "dT") D.dT = s; else if (v == "dc") D.dc = s;
+    else if (v == "k") { D.k = s; cnt = NM + h->M; } else if (v == "ds") { D.ds = s; cnt = NM + h->M; }
+    else if (v == "jH") { D.jH = s; cnt = NM + h->M; } else if (v == "jc") { D.jc = s; cnt = NM + h->M; }
+    else CGB_FAIL(h, CGB_ERR_INVALID, "unknown heat+salt diagnostic '%s'", var);
+    Diag dummy{};
+    int rc = salt_launch(h, t, true, dummy, &D);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(out, s, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return CGB_OK;
+}

@@ -6,7 +6,61 @@ import numpy as np
 from . import _lib as L
 
 
-class Engine:
+class _EngineBase:
+    """Methods shared by the heat and heat+salt engines (everything that does not depend on the state shape)."""
+
+    def _check(self, rc):
+        if rc != L.OK:
+            raise L.CgbError(rc, self.lib.cgb_last_error(self.h).decode())
+
+    def _param(self, name, arr, per):
+        a = L.as_f64(arr)
+        self._check(self.lib.cgb_set_param(self.h, name.encode(), L.dptr(a), a.size, per))
+
+    def status(self):
+        st = np.empty(self.M, dtype=np.int32); steps = np.empty(self.M, dtype=np.int64)
+        self._check(self.lib.cgb_get_status(self.h, st.ctypes.data_as(C.POINTER(C.c_int32)), steps.ctypes.data_as(C.POINTER(C.c_int64))))
+        return st, steps
+
+    def stats(self):
+        s = L.Stats()
+        self._check(self.lib.cgb_get_stats(self.h, C.byref(s)))
+        return {f[0]: getattr(s, f[0]) for f in L.Stats._fields_ if f[0] != "_pad"}
+
+    def advance_to(self, t_target, sync=True):
+        self._check(self.lib.cgb_advance_to(self.h, float(t_target)))
+        if sync:
+            self._check(self.lib.cgb_synchronize(self.h))
+
+    def synchronize(self):
+        self._check(self.lib.cgb_synchronize(self.h))
+
+    def device_pointers(self):
+        u, t, dt = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self.lib.cgb_device_state(self.h, C.byref(u), C.byref(t), C.byref(dt)))
+        return u.value, t.value, dt.value
+
+    def profile_enable(self, on=True):
+        self._check(self.lib.cgb_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        n = C.c_int64(0); ms = C.c_double(0.0)
+        self._check(self.lib.cgb_profile_read(self.h, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cgb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine(_EngineBase):
     """Thin, explicit wrapper over the C ABI. All arrays crossing it are host NumPy arrays, column-fastest."""
 
     def __init__(self, tile, stepper="euler", dt0=None, dtmin=1.0, dtmax=None, device=0,
@@ -45,14 +99,6 @@ class Engine:
         self._push_description()
 
     # ---- helpers
-    def _check(self, rc):
-        if rc != L.OK:
-            raise L.CgbError(rc, self.lib.cgb_last_error(self.h).decode())
-
-    def _param(self, name, arr, per):
-        a = L.as_f64(arr)
-        self._check(self.lib.cgb_set_param(self.h, name.encode(), L.dptr(a), a.size, per))
-
     def _push_description(self):
         t, cols = self.tile, self.columns
         e = L.as_f64(t.grid.edges)
@@ -104,29 +150,11 @@ class Engine:
         self._check(self.lib.cgb_get_state(self.h, L.dptr(u), L.dptr(t), L.dptr(dt)))
         return u, t, dt
 
-    def status(self):
-        st = np.empty(self.M, dtype=np.int32); steps = np.empty(self.M, dtype=np.int64)
-        self._check(self.lib.cgb_get_status(self.h, st.ctypes.data_as(C.POINTER(C.c_int32)), steps.ctypes.data_as(C.POINTER(C.c_int64))))
-        return st, steps
-
-    def stats(self):
-        s = L.Stats()
-        self._check(self.lib.cgb_get_stats(self.h, C.byref(s)))
-        return {f[0]: getattr(s, f[0]) for f in L.Stats._fields_ if f[0] != "_pad"}
-
     # ---- hot path
     def rhs(self, t):
         du = np.empty((self.N, self.M))
         self._check(self.lib.cgb_rhs(self.h, float(t), L.dptr(du)))
         return du
-
-    def advance_to(self, t_target, sync=True):
-        self._check(self.lib.cgb_advance_to(self.h, float(t_target)))
-        if sync:
-            self._check(self.lib.cgb_synchronize(self.h))
-
-    def synchronize(self):
-        self._check(self.lib.cgb_synchronize(self.h))
 
     def diag(self, var, t):
         n = self.N + 1 if var in ("k", "jH") else self.N
@@ -152,27 +180,3 @@ class Engine:
 
     def ensemble_partial_device(self, var, t, out_ptr):
         self._check(self.lib.cgb_ensemble_partial_device(self.h, var.encode(), float(t), C.c_void_p(out_ptr)))
-
-    def device_pointers(self):
-        u, t, dt = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        self._check(self.lib.cgb_device_state(self.h, C.byref(u), C.byref(t), C.byref(dt)))
-        return u.value, t.value, dt.value
-
-    def profile_enable(self, on=True):
-        self._check(self.lib.cgb_profile_enable(self.h, int(on)))
-
-    def profile_read(self):
-        n = C.c_int64(0); ms = C.c_double(0.0)
-        self._check(self.lib.cgb_profile_read(self.h, C.byref(n), C.byref(ms)))
-        return n.value, ms.value
-
-    def close(self):
-        if getattr(self, "h", None):
-            self.lib.cgb_destroy(self.h)
-            self.h = None
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass

@@ -273,3 +273,44 @@ def lite_advance_batch(tile, cols, H, t, dt, t_target, miniters=2, maxiters=1000
     st = lib().cg_lite_advance_batch(arr, len(ocs), dp(H), dp(t), dp(dt), float(t_target), miniters, maxiters, float(tol),
                                      ns.ctypes.data_as(_I64), it.ctypes.data_as(_I64), int(nthreads))
     return st, ns, it
+
+
+class OracleSaltColumn:
+    """One column of a SalineTile as the oracle's cg_salt_column (src/Physics/Salt restatement)."""
+
+    def __init__(self, tile, c=0):
+        self.tile = tile
+        n = tile.grid.ncells
+        self.n = n
+        self.edges = f64(tile.grid.edges); self.por = f64(tile.por_cell)
+        d = dict(kind=3, alpha=float(tile.sfcc.swrc.alpha), n=float(tile.sfcc.swrc.n), theta_res=float(tile.sfcc.swrc.theta_res),
+                 Tm=float(tile.sfcc.Tm), beta=1.0, omega=1.0)
+        self.col = SaltColumn(n=n, surface_state=int(tile.salt_bc.surfaceState), edges=dp(self.edges), por=dp(self.por),
+                              sat=tile.sat, org=tile.org, fc=fc_struct(d, solver=1), tp=thermal_struct(tile.tp),
+                              tau=tile.salt.prop.tau, ds0=tile.salt.prop.ds0, T_ub=tile.T_ub, benthic_salt=float(tile.benthic[c]),
+                              bot_value=-tile.Qgeo, courant=tile.salt.courant_number, dc_max=tile.salt.dc_max, heat_courant=0.5)
+        self.arrays = {}
+        self.w = SaltWork()
+        for name in SaltWork._names:
+            a = np.zeros(n + 1)
+            self.arrays[name] = a
+            setattr(self.w, name, dp(a))
+
+    def get(self, name):
+        m = self.n + 1 if name in ("k", "ds", "jH", "jc") else self.n
+        return self.arrays[name][:m].copy()
+
+    def rhs(self, T, c):
+        T, c = f64(T), f64(c)
+        lib().cg_salt_rhs(C.byref(self.col), dp(T), dp(c), C.byref(self.w))
+        return self.get("dT"), self.get("dc")
+
+    def timestep(self):
+        return lib().cg_salt_timestep(C.byref(self.col), C.byref(self.w))
+
+    def advance(self, T, c, t, dt, t_target, dtmin=1.0, dtmax=3600.0):
+        T, c = f64(T).copy(), f64(c).copy()
+        tt = np.array([t], dtype=np.float64); dd = np.array([dt], dtype=np.float64); ns = np.zeros(1, dtype=np.int64)
+        st = lib().cg_salt_advance(C.byref(self.col), dp(T), dp(c), dp(tt), dp(dd), float(t_target), float(dtmin), float(dtmax),
+                                   ns.ctypes.data_as(_I64), C.byref(self.w))
+        return T, c, tt[0], dd[0], int(ns[0]), st
