@@ -78,6 +78,7 @@ SIGNATURES = {
     "cgb_ensemble_partial_device": (C.c_int, [_P, C.c_char_p, C.c_double, _P]),
     "cgb_profile_enable": (C.c_int, [_P, C.c_int32]),
     "cgb_profile_read": (C.c_int, [_P, _I64, C.POINTER(C.c_double)]),
+    "cgb_selftest_rcp": (C.c_int, [_D, C.c_int64, _D, _D, _D]),
 }
 
 _lib = None

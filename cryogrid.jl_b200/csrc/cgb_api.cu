@@ -310,7 +310,7 @@ static int finalize(cgb_handle* h)
         std::vector<double> por = expand(h, h->params["por"], CGB_PER_COLUMN_LAYER), sat = expand(h, h->params["sat"], CGB_PER_COLUMN_LAYER);
         bool ok = true;
         for (size_t i = 0; i < por.size() && ok; ++i) ok = (por[i] * sat[i] >= 1e-8);
-        h->fast_ok = ok && (h->params.count("bot_value") || h->forc[1].kind == 0);
+        h->fast_ok = ok && (h->params.count("bot_value") || h->forc[1].kind == 0) && h->cfg.bot_kind == CGB_BC_NEUMANN;
     }
     up_cl("vg_alpha", &d.vg_alpha); up_cl("vg_n", &d.vg_n); up_cl("theta_res", &d.theta_res);
     up_cl("Tm", &d.Tm); up_cl("beta", &d.beta); up_cl("omega", &d.omega);
@@ -506,10 +506,17 @@ static int launch_advance(cgb_handle* h, double t_target)
     return rc;
 }
 
-template <int CPL, int MINB>
+static int fast_cubic()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("CGB_FAST_CUBIC"); v = e ? atoi(e) : 1; }
+    return v;
+}
+
+template <int CPL, int MINB, bool CUBIC>
 static int launch_fast_tb(cgb_handle* h, double t_target)
 {
-    auto kern = k_heat_euler_fast<CPL, MINB>;
+    auto kern = k_heat_euler_fast<CPL, MINB, CUBIC>;
     size_t smem = (size_t)(4 * h->nl * FC_STRIDE) * sizeof(double);
     static int blocks_per_sm = 0;   // per instantiation
     if (blocks_per_sm == 0) {
@@ -536,10 +543,17 @@ static int fast_minb()
 template <int CPL>
 static int launch_fast_t(cgb_handle* h, double t_target)
 {
+    if (fast_cubic()) {
+        switch (fast_minb()) {
+        case 2: return launch_fast_tb<CPL, 2, true>(h, t_target);
+        case 4: return launch_fast_tb<CPL, 4, true>(h, t_target);
+        default: return launch_fast_tb<CPL, 3, true>(h, t_target);
+        }
+    }
     switch (fast_minb()) {
-    case 2: return launch_fast_tb<CPL, 2>(h, t_target);
-    case 4: return launch_fast_tb<CPL, 4>(h, t_target);
-    default: return launch_fast_tb<CPL, 3>(h, t_target);
+    case 2: return launch_fast_tb<CPL, 2, false>(h, t_target);
+    case 4: return launch_fast_tb<CPL, 4, false>(h, t_target);
+    default: return launch_fast_tb<CPL, 3, false>(h, t_target);
     }
 }
 
@@ -778,4 +792,28 @@ extern "C" int cgb_profile_read(cgb_handle* h, int64_t* n_launches, double* tota
     *total_ms = tot;
     h->prof_events.clear();
     return CGB_OK;
+}
+
+// self-test of the reciprocal sequences used by the kernels (accuracy is asserted in tests/test_gpu_explicit.py)
+__global__ void k_selftest_rcp(const double* __restrict__ x, long long n, double* raw, double* n2, double* c3)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) { raw[i] = rcp_raw(x[i]); n2[i] = rcp_fast(x[i]); c3[i] = rcp_fast3(x[i]); }
+}
+
+extern "C" int cgb_selftest_rcp(const double* x, int64_t n, double* out_raw, double* out_newton2, double* out_cubic)
+{
+    if (!x || n < 1 || !out_raw || !out_newton2 || !out_cubic) return CGB_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return CGB_ERR_NO_DEVICE;
+    double* d = nullptr;
+    if (cudaMalloc((void**)&d, 4 * n * sizeof(double)) != cudaSuccess) return CGB_ERR_ALLOC;
+    cudaMemcpy(d, x, n * sizeof(double), cudaMemcpyHostToDevice);
+    k_selftest_rcp<<<(unsigned)((n + 255) / 256), 256>>>(d, n, d + n, d + 2 * n, d + 3 * n);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(out_raw, d + n, n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaMemcpy(out_newton2, d + 2 * n, n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaMemcpy(out_cubic, d + 3 * n, n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return e == cudaSuccess ? CGB_OK : CGB_ERR_CUDA;
 }

@@ -116,6 +116,35 @@ __device__ __forceinline__ double rcp_fast(double a)
     return y;
 }
 
+// Cubic (Halley-type) refinement: y1 = y0 (1 + e + e^2), e = 1 - a y0  -- 3 FMAs, error e0^3.
+__device__ __forceinline__ double rcp_fast3(double a)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = fma(-a, y, 1.0);
+    double p = fma(e, e, e);
+    return fma(y, p, y);
+}
+
+__device__ __forceinline__ double rcp_raw(double a)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    return y;
+}
+
+// min/max by compare+select (3 instructions; fmin/fmax cost ~7 on sm_100 because of their NaN-quieting sequence).
+// NaN in `a` is dropped (comparison false), like fmin/fmax with a non-NaN second operand.
+__device__ __forceinline__ double sel_max(double a, double b) { return (a > b) ? a : b; }
+__device__ __forceinline__ double sel_min(double a, double b) { return (a < b) ? a : b; }
+// max(x, 0) on the integer pipe: clear everything when the sign bit is set (-0.0 -> +0.0, NaN with sign -> 0)
+__device__ __forceinline__ double relu_bits(double x)
+{
+    int hi = __double2hiint(x), lo = __double2loint(x);
+    int m = ~(hi >> 31);
+    return __hiloint2double(hi & m, lo & m);
+}
+
 __device__ __forceinline__ double warp_max(double v)
 {
 #pragma unroll

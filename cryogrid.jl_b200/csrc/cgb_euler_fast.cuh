@@ -28,7 +28,10 @@ __device__ __forceinline__ double warp_max_nonneg(double v)
     return __hiloint2double((int)mhi, (int)mlo);
 }
 
-template <int CPL, int MINB>
+template <bool CUBIC>
+__device__ __forceinline__ double rcp_sel(double a) { return CUBIC ? rcp_fast3(a) : rcp_fast(a); }
+
+template <int CPL, int MINB, bool CUBIC>
 __global__ void __launch_bounds__(128, MINB) k_heat_euler_fast(const __grid_constant__ Dev P, double t_target)
 {
     extern __shared__ double smem[];
@@ -40,10 +43,10 @@ __global__ void __launch_bounds__(128, MINB) k_heat_euler_fast(const __grid_cons
 
     const double dC = P.ch_w - P.ch_i;
     const double dK = P.sk_w - P.sk_i;
-    const int jb = (N - 1) - lane * CPL;   // local slot of the bottom cell (if in [0,CPL))
 
     // static per-cell grid constants in registers
     double dk[CPL], idk[CPL], G[CPL], dk_up;
+    bool is_edgeN[CPL];   // this slot's upper edge is the bottom boundary (global edge index N)
     int loff[CPL];
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
@@ -53,12 +56,13 @@ __global__ void __launch_bounds__(128, MINB) k_heat_euler_fast(const __grid_cons
         idk[j] = cell ? P.inv_dk[i] : 0.0;
         G[j] = edge ? P.eG[i] : 0.0;
         loff[j] = P.cell_layer[cell ? i : N - 1] * FC_STRIDE;
+        is_edgeN[j] = (i == N);
     }
     {
         int i = lane * CPL - 1;
         dk_up = (i >= 0 && i < N) ? P.dk[i] : 1.0;
     }
-    const bool top_dirichlet = P.top_kind == 0, bot_dirichlet = P.bot_kind == 0, use_nf = P.use_nfactor != 0;
+    const bool top_dirichlet = P.top_kind == 0, use_nf = P.use_nfactor != 0;   // bottom: Neumann only (launcher)
     const int fkind = P.top.kind;
     const int fn = P.top.n;
     const double* __restrict__ ft = P.top.t;
@@ -100,6 +104,11 @@ __global__ void __launch_bounds__(128, MINB) k_heat_euler_fast(const __grid_cons
         double dt = P.dt[col];
         const double nf = P.nf[col], nt = P.nt[col], toff = P.top_offset[col];
         const double vbot = P.bot_value ? P.bot_value[col] : P.bot.value;   // launcher: bottom is constant in time here
+        // Neumann bottom flux enters as the additive term of the flux FMA of the slot below the last cell
+        double bflux[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) bflux[j] = is_edgeN[j] ? vbot : 0.0;
+        const double bflux_next = (lane * CPL + CPL == N) ? vbot : 0.0;   // bottom edge is slot 0 of the (absent or next) lane
         int status = 0;
         long long nsteps = 0;
         // forcing cursor (warp-uniform)
@@ -138,12 +147,12 @@ __global__ void __launch_bounds__(128, MINB) k_heat_euler_fast(const __grid_cons
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
                 const double* c = lcw + loff[j];
-                double hc = fmin(fmax(H[j], 0.0), c[FC_LTH]);
+                double hc = sel_min(relu_bits(H[j]), c[FC_LTH]);
                 double x = hc * c[FC_INVLTH];
                 double C = fma(c[FC_DCTH], x, c[FC_CB]);
                 double s = fma(c[FC_DKTH], x, c[FC_KB]);
                 kc[j] = s * s;
-                T[j] = (H[j] - hc) * rcp_fast(C);
+                T[j] = (H[j] - hc) * rcp_sel<CUBIC>(C);
             }
             // ---- stage B/C: edge fluxes (upper edge of every local cell)
             double Tup = __shfl_up_sync(FULL, T[CPL - 1], 1);
@@ -156,36 +165,32 @@ __global__ void __launch_bounds__(128, MINB) k_heat_euler_fast(const __grid_cons
                 double w1 = (j == 0) ? dk_up : dk[j - 1];
                 double den = fma(dk[j], k1, w1 * kc[j]);
                 double q = ((T1 - T[j]) * (k1 * kc[j])) * G[j];
-                je[j] = q * rcp_fast(den);
+                je[j] = fma(q, rcp_sel<CUBIC>(den), bflux[j]);   // q == 0 on the bottom edge (G = 0): je = -Qgeo there
             }
             if (lane == 0)   // heat_bc.jl:9-17 (Dirichlet) / methods.jl:156 (Neumann)
                 je[0] = top_dirichlet ? (kc[0] * (vtop - T[0])) * P.ctop : vtop;
             je[CPL] = __shfl_down_sync(FULL, je[0], 1);
+            if (bflux_next != 0.0 || lane == 31) je[CPL] = bflux_next;               // heat_bc.jl:32-35 / methods.jl:156
             // ---- divergence, limiter reduction, Euler update
             double maxabs = 0.0;
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
-                double jlow = je[j + 1];
-                if (j == jb) {   // heat_bc.jl:18-27,32-35
-                    jlow = bot_dirichlet ? (kc[j] * (T[j] - vbot)) * P.cbot : vbot;
-                    je[j + 1] = jlow;
-                }
-                double dH = (je[j] - jlow) * idk[j];
-                maxabs = fmax(maxabs, fabs(dH));
+                double dH = (je[j] - je[j + 1]) * idk[j];
+                maxabs = sel_max(fabs(dH), maxabs);
                 H[j] = fma(dt, dH, H[j]);                                            // basic_solvers.jl:66
             }
             maxabs = warp_max_nonneg(maxabs);
             t = t + dt;
             ++nsteps;
             // ---- next dt (basic_solvers.jl:76-77, heat_conduction.jl:183-191, steplimiters.jl:15-18), saveat! clip
-            double lim = (maxabs > 0.0) ? P.maxdelta * rcp_fast(maxabs) : INFINITY;
+            double lim = (maxabs > 0.0) ? P.maxdelta * rcp_fast(maxabs) : INFINITY;   // always 2 Newton steps here
             if (!(lim > 0.0) || !(lim < INFINITY)) {
                 lim = (maxabs > 0.0) ? P.maxdelta / maxabs : INFINITY;              // rare: exact path for extremes
                 if (!isfinite(lim) || !(lim > 0.0)) lim = INFINITY;
             }
-            double dtn = fmax(fmin(lim, P.dtmax), P.dtmin);
-            if (t < t_target) dtn = fmin(dtn, t_target - t);                         // integrator.jl:126-131
-            dt = fmin(P.dtmax, dtn);                                                  // integrator.jl:89
+            double dtn = sel_max(sel_min(lim, P.dtmax), P.dtmin);
+            double rem = t_target - t;
+            dt = (rem > 0.0) ? sel_min(dtn, rem) : dtn;                              // integrator.jl:126-131 (:89 is implied)
         }
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {

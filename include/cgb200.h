@@ -195,6 +195,9 @@ int cgb_ensemble_partial_device(cgb_handle* h, const char* var, double t, void* 
  * the last read, and resets. */
 int cgb_profile_enable(cgb_handle* h, int32_t on);
 int cgb_profile_read(cgb_handle* h, int64_t* n_launches, double* total_ms);
+/* Self-test: evaluates on the device the reciprocal sequences the kernels use in place of IEEE division
+ * (raw MUFU.RCP64H seed, seed + 2 Newton steps, seed + 1 cubic step) for n host inputs. */
+int cgb_selftest_rcp(const double* x, int64_t n, double* out_raw, double* out_newton2, double* out_cubic);
 
 #ifdef __cplusplus
 }

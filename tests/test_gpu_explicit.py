@@ -284,3 +284,18 @@ def test_ensemble_partial_sums():
     np.testing.assert_allclose(s, T.sum(axis=1), rtol=1e-12, atol=1e-9)
     np.testing.assert_allclose(q, (T * T).sum(axis=1), rtol=1e-12, atol=1e-9)
     eng.close()
+
+
+def test_reciprocal_sequences_accuracy():
+    # the kernels replace IEEE division by MUFU.RCP64H + Newton; check the error against 1/x over the operand ranges
+    # that occur (heat capacities ~1e6, conductivity denominators ~1e-2..1e2, |dH| ~1e-6..1e6)
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(1e5, 5e6, 20000), 10.0 ** rng.uniform(-8, 8, 20000), 1.0 + rng.uniform(0, 1, 20000)])
+    lib = L.load()
+    raw, n2, c3 = np.empty_like(x), np.empty_like(x), np.empty_like(x)
+    assert lib.cgb_selftest_rcp(L.dptr(x), x.size, L.dptr(raw), L.dptr(n2), L.dptr(c3)) == 0
+    ref = 1.0 / x
+    e_raw, e_n2, e_c3 = (np.max(np.abs(v - ref) / ref) for v in (raw, n2, c3))
+    print(f"rcp rel. error: raw {e_raw:.3e} (2^{np.log2(e_raw):.1f}), newton2 {e_n2:.3e}, cubic {e_c3:.3e}")
+    assert e_n2 < 3e-16          # <= ~1.3 ulp
+    assert e_raw < 2.0 ** -16
