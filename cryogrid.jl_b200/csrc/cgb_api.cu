@@ -334,7 +334,12 @@ static int finalize(cgb_handle* h)
             double *pt, *py;
             rc |= dev_upload(h, &pt, f.t); rc |= dev_upload(h, &py, f.y);
             F.t = pt; F.y = py;
-        }
+            if (w == 0) {
+                std::vector<double> inv(f.t.size() - 1);
+                for (size_t k = 0; k + 1 < f.t.size(); ++k) inv[k] = 1.0 / (f.t[k + 1] - f.t[k]);
+                double* pi; rc |= dev_upload(h, &pi, inv); d.top_inv_dt = pi;
+            }
+        } else if (w == 0) d.top_inv_dt = nullptr;
         (w == 0 ? d.top : d.bot) = F;
     }
     d.maxdelta = h->cfg.maxdelta; d.courant = h->cfg.courant; d.dtmin = h->cfg.dtmin; d.dtmax = h->cfg.dtmax;

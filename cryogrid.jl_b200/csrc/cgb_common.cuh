@@ -76,6 +76,7 @@ struct Dev {
     // boundary conditions
     int top_kind, bot_kind, use_nfactor, limiter;
     Forcing top, bot;
+    const double* top_inv_dt; // [top.n-1] 1/(t[k+1]-t[k]) of the top forcing table (or nullptr)
     const double *nf, *nt, *top_offset, *bot_value;   // [M] (bot_value may be nullptr -> forcing)
     double maxdelta, courant, dtmin, dtmax;
     int lite_miniters, lite_maxiters; double lite_tol;

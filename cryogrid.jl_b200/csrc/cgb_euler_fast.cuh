@@ -111,39 +111,41 @@ __global__ void __launch_bounds__(128, MINB) k_heat_euler_fast(const __grid_cons
         const double bflux_next = (lane * CPL + CPL == N) ? vbot : 0.0;   // bottom edge is slot 0 of the (absent or next) lane
         int status = 0;
         long long nsteps = 0;
-        // forcing cursor (warp-uniform)
+        // forcing cursor (warp-uniform); finv = 1/(t[k+1]-t[k]) comes from a host-built table (no division in the loop)
         int fidx = 0;
         double fta = 0.0, ftb = 0.0, fya = 0.0, fyb = 0.0, finv = 0.0;
+        const double* __restrict__ fiv = P.top_inv_dt;
         if (fkind == 2) {
             double ts = fmin(fmax(t, ft_first), ft_last);
             int lo = 0, hi = fn - 1;
             while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (__ldg(ft + mid) <= ts) lo = mid; else hi = mid; }
             fidx = lo; fta = __ldg(ft + lo); ftb = __ldg(ft + lo + 1); fya = __ldg(fy + lo); fyb = __ldg(fy + lo + 1);
-            finv = 1.0 / (ftb - fta);
+            finv = __ldg(fiv + lo);
         }
-
-        while (t < t_target) {
-            // ---- upper boundary value at the START of the step (basic_solvers.jl:61-63)
-            double vtop;
+        // upper boundary value at time tq (warp-uniform).  Out-of-range times are clamped here; the BoundsError status is
+        // raised at the top of the step that would actually use them.
+        auto top_value = [&](double tq) -> double {
+            double v;
             if (fkind == 2) {
-                if (t < ft_first || t > ft_last) { status |= 4; break; }                 // providers.jl:30-33
-                while (t >= ftb && fidx < fn - 2) {
+                double tc = sel_min(sel_max(tq, ft_first), ft_last);
+                while (tc >= ftb && fidx < fn - 2) {
                     ++fidx; fta = ftb; fya = fyb;
-                    ftb = __ldg(ft + fidx + 1); fyb = __ldg(fy + fidx + 1);
-                    finv = 1.0 / (ftb - fta);
+                    ftb = __ldg(ft + fidx + 1); fyb = __ldg(fy + fidx + 1); finv = __ldg(fiv + fidx);
                 }
-                double w = (t - fta) * finv;
-                vtop = fma(w, fyb, (1.0 - w) * fya);
+                double w = (tc - fta) * finv;
+                v = fma(w, fyb, (1.0 - w) * fya);
             } else if (fkind == 1) {
-                vtop = P.top.amplitude * sin(2.0 * M_PI * (t / P.top.period) + P.top.phase) + P.top.level;   // simple_bc.jl:37
+                v = P.top.amplitude * sin(2.0 * M_PI * (tq / P.top.period) + P.top.phase) + P.top.level;   // simple_bc.jl:37
             } else {
-                vtop = P.top.value;
+                v = P.top.value;
             }
-            vtop += toff;
-            if (top_dirichlet && use_nf) vtop = ((vtop <= 0.0) ? nf : nt) * vtop;     // heat_bc.jl:78-86
-
-            // ---- stage A: H -> T, kc   (heat_conduction.jl:18-57, thermal_properties.jl:37)
-            double T[CPL], kc[CPL];
+            v += toff;
+            if (top_dirichlet && use_nf) v = ((v <= 0.0) ? nf : nt) * v;             // heat_bc.jl:78-86
+            return v;
+        };
+        // H -> T, kc for all local cells (heat_conduction.jl:18-57, thermal_properties.jl:37)
+        double T[CPL], kc[CPL];
+        auto stage_a = [&]() {
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
                 const double* c = lcw + loff[j];
@@ -154,7 +156,15 @@ __global__ void __launch_bounds__(128, MINB) k_heat_euler_fast(const __grid_cons
                 kc[j] = s * s;
                 T[j] = (H[j] - hc) * rcp_sel<CUBIC>(C);
             }
-            // ---- stage B/C: edge fluxes (upper edge of every local cell)
+        };
+
+        // Software-pipelined step loop: the diagnostics (stage A) and the boundary value of step n+1 are computed while
+        // the warp reduction and the reciprocal of step n's limiter are in flight -- they do not depend on dt_{n+1}.
+        double vtop = top_value(t);
+        stage_a();
+        while (t < t_target) {
+            if (fkind == 2 && (t < ft_first || t > ft_last)) { status |= 4; break; }     // providers.jl:30-33
+            // ---- edge fluxes (upper edge of every local cell): harmonic mean + flux with one reciprocal
             double Tup = __shfl_up_sync(FULL, T[CPL - 1], 1);
             double kup = __shfl_up_sync(FULL, kc[CPL - 1], 1);
             double je[CPL + 1];
@@ -172,25 +182,37 @@ __global__ void __launch_bounds__(128, MINB) k_heat_euler_fast(const __grid_cons
             je[CPL] = __shfl_down_sync(FULL, je[0], 1);
             if (bflux_next != 0.0 || lane == 31) je[CPL] = bflux_next;               // heat_bc.jl:32-35 / methods.jl:156
             // ---- divergence, limiter reduction, Euler update
-            double maxabs = 0.0;
+            double ad[CPL];
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
                 double dH = (je[j] - je[j + 1]) * idk[j];
-                maxabs = sel_max(fabs(dH), maxabs);
+                ad[j] = fabs(dH);
                 H[j] = fma(dt, dH, H[j]);                                            // basic_solvers.jl:66
             }
-            maxabs = warp_max_nonneg(maxabs);
-            t = t + dt;
+            // max |dH| over the local cells as a tree (depth log2 CPL instead of CPL dependent compares); NaN is dropped
+#pragma unroll
+            for (int w = 1; w < CPL; w *= 2)
+#pragma unroll
+                for (int j = 0; j + w < CPL; j += 2 * w) ad[j] = sel_max(ad[j + w], ad[j]);
+            double maxabs = sel_max(ad[0], 0.0);
+            // start the warp reduction (integer REDUX unit) ...
+            unsigned mh = (unsigned)__double2hiint(maxabs), ml = (unsigned)__double2loint(maxabs);
+            unsigned rh = __reduce_max_sync(FULL, mh);
+            unsigned rl = __reduce_max_sync(FULL, mh == rh ? ml : 0u);
+            const double tn = t + dt;
             ++nsteps;
+            // ... and overlap it with the next step's boundary value and diagnostics
+            vtop = top_value(tn);
+            stage_a();
             // ---- next dt (basic_solvers.jl:76-77, heat_conduction.jl:183-191, steplimiters.jl:15-18), saveat! clip
-            double lim = (maxabs > 0.0) ? P.maxdelta * rcp_fast(maxabs) : INFINITY;   // always 2 Newton steps here
-            if (!(lim > 0.0) || !(lim < INFINITY)) {
-                lim = (maxabs > 0.0) ? P.maxdelta / maxabs : INFINITY;              // rare: exact path for extremes
-                if (!isfinite(lim) || !(lim > 0.0)) lim = INFINITY;
-            }
+            maxabs = __hiloint2double((int)rh, (int)rl);
+            double mc = sel_min(sel_max(maxabs, 1e-300), 1e300);                     // keeps the reciprocal finite
+            double lim = P.maxdelta * rcp_fast(mc);                                  // 2 Newton steps: correctly rounded 1/x
+            if (maxabs == INFINITY) lim = INFINITY;                                  // |Δmax/inf| = 0 -> "not > 0" -> Inf
             double dtn = sel_max(sel_min(lim, P.dtmax), P.dtmin);
-            double rem = t_target - t;
+            double rem = t_target - tn;
             dt = (rem > 0.0) ? sel_min(dtn, rem) : dtn;                              // integrator.jl:126-131 (:89 is implied)
+            t = tn;
         }
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
