@@ -4,6 +4,7 @@
 #include "cgb_euler.cuh"
 #include "cgb_euler_fast.cuh"
 #include "cgb_lite.cuh"
+#include "cgb_lite_warp.cuh"
 #include "cgb_salt.cuh"
 
 using namespace cgb;
@@ -583,7 +584,13 @@ static int launch_advance_inner(cgb_handle* h, double t_target)
 {
     Diag D{};
     if (h->cfg.physics == CGB_PHYSICS_HEAT_SALT) return salt_launch(h, t_target, false, D, nullptr);
-    if (h->cfg.stepper == CGB_STEPPER_LITE_IMPLICIT) return lite_launch(h, t_target, false, D);
+    if (h->cfg.stepper == CGB_STEPPER_LITE_IMPLICIT) {
+        // "Thomas per thread or partition/PCR per warp": the warp variant is the default; CGB_LITE_VARIANT=thread selects
+        // the reference-order Thomas sweep (re-read on every launch so that tests can switch in-process)
+        const char* v = getenv("CGB_LITE_VARIANT");
+        if (v && std::strcmp(v, "thread") == 0) return lite_launch(h, t_target, false, D);
+        return lite_warp_launch(h, t_target);
+    }
     bool fast = all_freewater(h) && h->cfg.limiter == CGB_LIMITER_MAXDELTA && h->fast_ok;
     return fast ? launch_fast(h, t_target) : launch_euler_c<false, false>(h, t_target, D);
 }

@@ -1,0 +1,271 @@
+// cgb_lite_warp.cuh -- LiteImplicitEuler, variant "warp per column": register-resident Picard iteration with a
+// partitioned tridiagonal solve across the 32 lanes of a warp.
+//
+// Why: with one thread per column (cgb_lite.cuh) a launch lasts as long as its slowest column and a warp iterates until
+// its slowest lane converges.  Here one WARP owns one column (lane l holds rows [l*CPL, (l+1)*CPL)), H, H0, T, dH/dT and
+// the system rows stay in registers for all Picard iterations and all time steps of a save interval, columns are
+// fetched from a global cursor, and the iteration count is warp-uniform by construction.
+//
+// Tridiagonal solve (replaces the sequential Thomas sweep of Numerics/math.jl:169-197; same linear system, rows
+// assembled exactly as cglite_step.jl:81-99): Wang-type partition --
+//   1. local forward elimination   (row j couples to x_p = last unknown of the previous lane, x_j, x_{j+1})
+//   2. local backward elimination  (row j couples to x_p, x_j and the lane's last unknown x_{m-1})
+//   3. reduced 32-unknown system in the lanes' last unknowns, solved by parallel cyclic reduction with shuffles
+//   4. local back-substitution.
+// The matrices are strictly diagonally dominant (B = ap + dH/dT/dt > an + as), so no pivoting is needed; results differ
+// from the Thomas order by rounding only (checked against the oracle in tests/test_gpu_lite.py).
+#pragma once
+#include "cgb_handle.h"
+#include "cgb_euler.cuh"
+
+namespace cgb {
+
+template <int CPL>
+__global__ void __launch_bounds__(128, 2) k_lite_warp(const __grid_constant__ Dev P, double t_target)
+{
+    extern __shared__ double smem[];
+    double* sDk = smem;                    // [CPL*32] cell thickness (1 for padding)
+    double* sIdk = sDk + CPL * 32;         // 1/dk (0 for padding)
+    double* sW1 = sIdk + CPL * 32;         // harmonic-mean weights of the upper edge
+    double* sW2 = sW1 + CPL * 32;
+    double* sG = sW2 + CPL * 32;           // (w1+w2)/dxc of the upper edge (0 for non-interior edges)
+    double* sLCall = sG + CPL * 32;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int N = P.N;
+    const long long M = P.M;
+    double* lcw = sLCall + warp * (P.n_layers * LC_STRIDE);
+    for (int s = threadIdx.x; s < CPL * 32; s += blockDim.x) {
+        int j = s >> 5, ln = s & 31;
+        int i = ln * CPL + j;
+        bool cell = i < N, edge = (i > 0 && i < N);
+        sDk[s] = cell ? P.dk[i] : 1.0;
+        sIdk[s] = cell ? P.inv_dk[i] : 0.0;
+        sW1[s] = edge ? P.eW1[i] : 1.0;
+        sW2[s] = edge ? P.eW2[i] : 1.0;
+        sG[s] = edge ? P.eG[i] : 0.0;
+    }
+    __syncthreads();
+    const double dC = P.ch_w - P.ch_i, dK = P.sk_w - P.sk_i;
+    int loff[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+        int i = lane * CPL + j;
+        loff[j] = P.cell_layer[i < N ? i : N - 1] * LC_STRIDE;
+    }
+    const int jb = (N - 1) - lane * CPL;                 // local slot of the bottom row
+    const int ef = P.bot_layer_first;                    // heat_implicit.jl:83 quirk: k[first edge of the bottom layer]
+
+    for (;;) {
+        unsigned long long cu = 0;
+        if (lane == 0) cu = atomicAdd(P.counter, 1ull);
+        cu = __shfl_sync(FULL, cu, 0);
+        if (cu >= (unsigned long long)M) break;
+        const long long col = (long long)cu;
+        __syncwarp();
+        stage_layer_consts(P, col, lcw, lane);
+        __syncwarp();
+
+        double H[CPL], H0[CPL], T[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            int i = lane * CPL + j;
+            H[j] = (i < N) ? P.u[(size_t)i * M + col] : 0.0;
+            T[j] = H[j] / P.ch_w;
+        }
+        double t = P.t[col], dt = P.dt[col];
+        const double nf = P.nf[col], nt = P.nt[col], toff = P.top_offset[col];
+        int status = 0;
+        long long nsteps = 0, niter = 0;
+        ForcingCursor ctop, cbot;
+        if (P.top.kind == 2) forcing_seek(P.top, ctop, fmin(fmax(t, __ldg(P.top.t)), __ldg(P.top.t + P.top.n - 1)));
+        if (P.bot.kind == 2 && !P.bot_value) forcing_seek(P.bot, cbot, fmin(fmax(t, __ldg(P.bot.t)), __ldg(P.bot.t + P.bot.n - 1)));
+
+        while (t < t_target) {
+            const double tn = t + dt;                                               // cglite_step.jl:9
+            double vtop = forcing_eval(P.top, ctop, tn, status) + toff;
+            if (P.top_kind == 0 && P.use_nfactor) vtop = ((vtop <= 0.0) ? nf : nt) * vtop;
+            const double vbot = P.bot_value ? P.bot_value[col] : forcing_eval(P.bot, cbot, tn, status);
+            if (status & 4) break;
+            const double idt = 1.0 / dt;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) H0[j] = H[j];                              // cache.uprev
+            int iter = 1;
+            double emax = INFINITY;
+            while ((emax > P.lite_tol && iter <= P.lite_maxiters) || iter < P.lite_miniters) {   // cglite_step.jl:43
+                // ---- diagnostics
+                double kc[CPL], dHdT[CPL];
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) {
+                    double thw, C, dth;
+                    freezethaw_cell<false>(P, lcw + loff[j], H[j], dC, dK, T[j], thw, C, dHdT[j], dth, kc[j]);
+                }
+                // ---- kd = k_edge/dxc on the upper edge of every local cell (harmonic mean, math.jl:141)
+                double kup = __shfl_up_sync(FULL, kc[CPL - 1], 1);
+                double kd[CPL + 1];
+                double kfirst = 0.0;   // k on edge `ef` (Dirichlet bottom quirk only)
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) {
+                    double k1 = (j == 0) ? kup : kc[j - 1];
+                    int s = j * 32 + lane;
+                    double w1 = sW1[s], w2 = sW2[s], g = sG[s];
+                    double r = rcp_fast(fma(w2, k1, w1 * kc[j]));
+                    double kk = k1 * kc[j];
+                    kd[j] = (kk * g) * r;                                            // 0 on non-interior edges
+                    if (P.bot_kind == 0 && lane * CPL + j == ef) kfirst = (ef == 0) ? kc[j] : (kk * (w1 + w2)) * r;
+                }
+                kd[CPL] = __shfl_down_sync(FULL, kd[0], 1);
+                if (lane == 31) kd[CPL] = 0.0;
+                if (P.bot_kind == 0) kfirst = __shfl_sync(FULL, kfirst, ef / CPL);
+                // ---- rows: A = -an, B = ap + dHdT/dt, C = -as, D = (H0-H)/dt + dHdT/dt*T + bp   (cglite_step.jl:81-99)
+                double fa[CPL], gc[CPL], rb[CPL], d[CPL];
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) {
+                    int s = j * 32 + lane;
+                    double idk = sIdk[s];
+                    double an = kd[j] * idk, as = kd[j + 1] * idk;                   // heat_implicit.jl:10-24
+                    if (j == jb) as = 0.0;
+                    double ap = an + as, bp = 0.0;
+                    if (j == 0 && lane == 0) {                                       // heat_implicit.jl:59-64,72-79
+                        double dk = sDk[s];
+                        double jtop = (P.top_kind == 0) ? 2.0 * vtop * kc[0] * idk : vtop;
+                        bp += jtop * idk;
+                        if (P.top_kind == 0) ap += kc[0] / (dk * dk / 2.0);
+                    }
+                    if (j == jb) {                                                   // heat_implicit.jl:65-70,80-86 (quirks verbatim)
+                        double dk = sDk[s];
+                        double jbot = (P.bot_kind == 0) ? 2.0 * vbot * kc[j] * idk : vbot;
+                        bp += jbot * idk;
+                        if (P.bot_kind == 0) ap += kfirst / (dk * dk / 2.0);
+                    }
+                    double sp = dHdT[j] * idt;                                       // -Sp
+                    bool real = (lane * CPL + j) < N;
+                    fa[j] = real ? -an : 0.0;
+                    gc[j] = real ? -as : 0.0;
+                    rb[j] = real ? ap + sp : 1.0;                                    // B (reciprocal taken below)
+                    d[j] = real ? fma(sp, T[j], (H0[j] - H[j]) * idt) + bp : 0.0;
+                }
+                // ---- 1. forward elimination: row j -> f_j x_p + b_j x_j + c_j x_{j+1} = d_j
+                rb[0] = rcp_fast(rb[0]);
+#pragma unroll
+                for (int j = 1; j < CPL; ++j) {
+                    double w = fa[j] * rb[j - 1];
+                    fa[j] = -w * fa[j - 1];
+                    d[j] = fma(-w, d[j - 1], d[j]);
+                    rb[j] = rcp_fast(fma(-w, gc[j - 1], rb[j]));
+                }
+                // ---- 2. backward elimination: row j -> f_j x_p + b_j x_j + g_j x_{m-1} = d_j   (j <= m-2)
+                const double c_last = gc[CPL - 1];
+#pragma unroll
+                for (int j = CPL - 3; j >= 0; --j) {
+                    double w = gc[j] * rb[j + 1];
+                    fa[j] = fma(-w, fa[j + 1], fa[j]);
+                    d[j] = fma(-w, d[j + 1], d[j]);
+                    gc[j] = -w * gc[j + 1];
+                }
+                // ---- 3. reduced system in y_l = x_{m-1} of lane l; x_0 of lane l+1 = (d0 - f0 y_l - g0 y_{l+1}) / b0
+                double rf, rg, rd;
+                if (CPL >= 2) { rf = fa[0] * rb[0]; rg = gc[0] * rb[0]; rd = d[0] * rb[0]; }
+                else { rf = 0.0; rg = 0.0; rd = 0.0; }
+                double nf0 = __shfl_down_sync(FULL, rf, 1), ng0 = __shfl_down_sync(FULL, rg, 1), nd0 = __shfl_down_sync(FULL, rd, 1);
+                double A, B, C, D;
+                if (CPL >= 2) {
+                    A = fa[CPL - 1];
+                    B = fma(-c_last, nf0, 1.0 / rb[CPL - 1]);
+                    C = -c_last * ng0;
+                    D = fma(-c_last, nd0, d[CPL - 1]);
+                } else {   // one row per lane: the reduced system is the system itself
+                    A = fa[0]; B = 1.0 / rb[0]; C = c_last; D = d[0];
+                }
+                if (lane == 31) C = 0.0;
+                if (lane == 0) A = 0.0;
+#pragma unroll
+                for (int s = 1; s < 32; s <<= 1) {                                   // parallel cyclic reduction
+                    double rB = rcp_fast(B);
+                    double Au = __shfl_up_sync(FULL, A, s), Cu = __shfl_up_sync(FULL, C, s), Du = __shfl_up_sync(FULL, D, s), rBu = __shfl_up_sync(FULL, rB, s);
+                    double Ad = __shfl_down_sync(FULL, A, s), Cd = __shfl_down_sync(FULL, C, s), Dd = __shfl_down_sync(FULL, D, s), rBd = __shfl_down_sync(FULL, rB, s);
+                    bool hu = lane >= s, hd = lane + s < 32;
+                    double al = hu ? -A * rBu : 0.0, ga = hd ? -C * rBd : 0.0;
+                    B = B + al * (hu ? Cu : 0.0) + ga * (hd ? Ad : 0.0);
+                    D = D + al * (hu ? Du : 0.0) + ga * (hd ? Dd : 0.0);
+                    A = al * (hu ? Au : 0.0);
+                    C = ga * (hd ? Cd : 0.0);
+                }
+                const double y = D * rcp_fast(B);
+                double xp = __shfl_up_sync(FULL, y, 1);
+                if (lane == 0) xp = 0.0;
+                // ---- 4. back-substitution + Picard update (cglite_step.jl:58-72)
+                double em = 0.0;
+                bool bad = false;
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) {
+                    double x;
+                    if (CPL >= 2) x = (j == CPL - 1) ? y : (d[j] - fa[j] * xp - gc[j] * y) * rb[j];
+                    else x = y;
+                    if ((lane * CPL + j) < N) {
+                        double e = x - T[j];
+                        H[j] = fma(dHdT[j], e, H[j]);
+                        em = sel_max(fabs(e), em);
+                        bad |= !isfinite(e);
+                    }
+                }
+                emax = warp_max(em);
+                ++niter; ++iter;
+                if (__any_sync(FULL, bad)) { status |= 2; break; }
+            }
+            if (iter > P.lite_maxiters && emax > P.lite_tol) status |= 1;           // cglite_step.jl:74-77
+            t = tn; ++nsteps;
+            if (t < t_target) dt = fmin(dt, t_target - t);                          // integrator.jl:126-131
+            dt = fmin(P.dtmax, dt);
+            if (status & 2) break;
+        }
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            int i = lane * CPL + j;
+            if (i < N) P.u[(size_t)i * M + col] = H[j];
+        }
+        if (lane == 0) {
+            P.t[col] = t; P.dt[col] = dt; P.steps[col] += nsteps; P.iters[col] += niter;
+            if (status) P.status[col] |= status;
+        }
+    }
+}
+
+} // namespace cgb
+
+template <int CPL>
+static int lite_warp_launch_t(cgb_handle* h, double t_target)
+{
+    using namespace cgb;
+    auto kern = k_lite_warp<CPL>;
+    size_t smem = (size_t)(5 * CPL * 32 + 4 * h->nl * LC_STRIDE) * sizeof(double);
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, 128, smem));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    long long grid = std::min<long long>((h->M + 3) / 4, (long long)h->num_sms * blocks_per_sm);
+    CUDA_TRY(h, cudaMemsetAsync(h->dev.counter, 0, sizeof(unsigned long long), h->stream));
+    kern<<<(unsigned)grid, 128, smem, h->stream>>>(h->dev, t_target);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return CGB_OK;
+}
+
+static int lite_warp_launch(cgb_handle* h, double t_target)
+{
+    int cpl = (h->N + 31) / 32;
+    switch (cpl) {
+    case 1: return lite_warp_launch_t<1>(h, t_target);
+    case 2: return lite_warp_launch_t<2>(h, t_target);
+    case 3: case 4: return lite_warp_launch_t<4>(h, t_target);
+    case 5: case 6: return lite_warp_launch_t<6>(h, t_target);
+    case 7: return lite_warp_launch_t<7>(h, t_target);
+    case 8: return lite_warp_launch_t<8>(h, t_target);
+    case 9: return lite_warp_launch_t<9>(h, t_target);
+    case 10: return lite_warp_launch_t<10>(h, t_target);
+    case 11: case 12: return lite_warp_launch_t<12>(h, t_target);
+    default: return lite_warp_launch_t<16>(h, t_target);
+    }
+}

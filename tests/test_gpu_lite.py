@@ -1,5 +1,7 @@
 """GPU parity tests of the implicit (LiteImplicitEuler / CryoGridLite) path against the CPU oracle, plus the
 reference's own analytic acceptance tests (test/Solvers/cglite_implicit_tests.jl) run through the CUDA path."""
+import os
+
 import numpy as np
 import pytest
 
@@ -7,6 +9,18 @@ import common
 import cryogrid_jl_b200 as cg
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=["warp", "thread"])
+def variant(request):
+    """Both batched-tridiagonal variants: partition/PCR per warp (default) and the reference-order Thomas per thread."""
+    old = os.environ.get("CGB_LITE_VARIANT")
+    os.environ["CGB_LITE_VARIANT"] = request.param
+    yield request.param
+    if old is None:
+        del os.environ["CGB_LITE_VARIANT"]
+    else:
+        os.environ["CGB_LITE_VARIANT"] = old
 
 
 def test_lite_diag_coefficients(orc):
@@ -27,7 +41,7 @@ def test_lite_diag_coefficients(orc):
     eng.close()
 
 
-def test_lite_one_year_ensemble(orc):
+def test_lite_one_year_ensemble(orc, variant):
     # cfg3 shape at test size: daily steps for one year; <= 1e-6 K and <= 1e-8 θw against the oracle, equal iteration counts
     tile = common.lite_ensemble_tile(ncolumns=9, seed=1234)
     H0 = cg.initialcondition(tile)
@@ -52,11 +66,15 @@ def test_lite_one_year_ensemble(orc):
             assert np.max(np.abs(Tg[:, c] - oc.work.get("T"))) <= 1e-6
             assert np.max(np.abs(thwg[:, c] - oc.work.get("thw"))) <= 1e-8
     total_iters = sum(v[4] for v in ref.values())
-    assert eng.stats()["lite_iterations"] == total_iters
+    got = eng.stats()["lite_iterations"]
+    if variant == "thread":
+        assert got == total_iters          # same operation order as the reference: identical Picard trajectories
+    else:
+        assert abs(got - total_iters) <= max(1, 1e-3 * total_iters)   # rounding may flip a borderline convergence test
     eng.close()
 
 
-def test_lite_periodic_analytic_on_gpu():
+def test_lite_periodic_analytic_on_gpu(variant):
     # test/Solvers/cglite_implicit_tests.jl:14-46 through the CUDA path
     P, A, T0 = common.YEAR, 1.0, 1.0
     heat = cg.HeatBalance(op="implicit")
@@ -77,7 +95,7 @@ def test_lite_periodic_analytic_on_gpu():
     assert np.max(np.abs(err)) < 0.01
 
 
-def test_lite_stefan_on_gpu():
+def test_lite_stefan_on_gpu(variant):
     # test/Solvers/cglite_implicit_tests.jl:49-88 through the CUDA path (thaw depth vs Neumann solution < 0.01 m)
     from test_oracle_golden import _stefan_lambda
     heat = cg.HeatBalance(op="implicit")
@@ -96,7 +114,7 @@ def test_lite_stefan_on_gpu():
     assert np.max(np.abs(td - 2 * lam * np.sqrt(a_l * sol.t))) < 0.01
 
 
-def test_lite_maxiters_status():
+def test_lite_maxiters_status(variant):
     tile = common.lite_ensemble_tile(ncolumns=4, seed=7)
     H0 = cg.initialcondition(tile)
     eng = cg.Engine(tile, stepper="lite", maxiters=1, tolerance=1e-12, miniters=1)
@@ -105,3 +123,32 @@ def test_lite_maxiters_status():
     st, steps = eng.status()
     assert np.all(st & 1) and np.all(steps == 30)     # ReturnCode.MaxIters, cglite_step.jl:74-77
     eng.close()
+
+
+@pytest.mark.parametrize("grid_name", ["DefaultGrid_1m", "DefaultGrid_20cm", "DefaultGrid_5cm"])
+def test_lite_warp_vs_thread_other_grids(orc, grid_name):
+    # different cells-per-lane instantiations of the warp kernel against the oracle (Dirichlet bottom: heat_implicit.jl:83 quirk)
+    grid = getattr(cg, grid_name)
+    heat = cg.HeatBalance(op="implicit")
+    layers = [(0.0, cg.Ground(cg.SimpleSoil(por=np.array([0.6, 0.4, 0.5]), org=0.3), heat=heat)),
+              (1.0, cg.Ground(cg.SimpleSoil(por=0.35), heat=heat)), (20.0, cg.Ground(cg.SimpleSoil(por=0.1), heat=heat))]
+    strat = cg.Stratigraphy((0.0, cg.Top(cg.PeriodicBC(cg.Dirichlet, common.YEAR, 12.0, 0.5, -3.0))), layers,
+                            (1000.0, cg.Bottom(cg.ConstantBC(cg.Dirichlet, 9.0))))
+    tile = cg.Tile(strat, grid, None, cg.initializer("T", cg.TemperatureProfile((0.0, -4.0), (10.0, -2.0), (1000.0, 9.0))), ncolumns=3)
+    H0 = cg.initialcondition(tile)
+    os.environ["CGB_LITE_VARIANT"] = "warp"
+    try:
+        eng = cg.Engine(tile, stepper="lite")
+        eng.set_state(H0, 0.0)
+        eng.advance_to(60 * 86400.0)
+        T = eng.diag("T", 60 * 86400.0)
+        st, steps = eng.status()
+        assert not st.any() and np.all(steps == 60)
+        for c in range(tile.M):
+            oc = orc.OracleColumn(tile, c)
+            Hr, *_ = oc.lite_advance(H0[:, c], 0.0, 86400.0, 60 * 86400.0)
+            oc.rhs(Hr, 60 * 86400.0)
+            assert np.max(np.abs(T[:, c] - oc.work.get("T"))) <= 1e-6
+        eng.close()
+    finally:
+        del os.environ["CGB_LITE_VARIANT"]
