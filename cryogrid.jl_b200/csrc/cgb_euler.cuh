@@ -71,37 +71,53 @@ __device__ __forceinline__ void stage_layer_consts(const Dev& P, long long col, 
     for (int l = lane; l < P.n_layers; l += 32) layer_consts(P, col, l, lc + l * LC_STRIDE);
 }
 
-// Tightly converged safeguarded Newton for T*C(θw(T)) + Lθw(T) = H (same algorithm as the oracle).
-__device__ __forceinline__ double sfcc_newton(const double* lc, double L, double dC, double H, double T0)
+// Safeguarded Newton for T*C(θw(T)) + Lθw(T) = H (monotone in T; same bracketing as the oracle).
+// EXACT: iterate to 1e-15 relative and re-evaluate θw at the root (diagnostics: bitwise-comparable with the oracle's
+// procedure).  Otherwise (stepping): stop once |ΔT| <= 1e-9 -- Newton is quadratic, so the accepted T is accurate to
+// ~1e-15 -- and carry θw, C to the new T with a first-order correction instead of another 2-exp/2-log evaluation.
+template <bool EXACT>
+__device__ __forceinline__ void sfcc_newton_solve(const double* lc, double L, double dC, double H, double& T, double& thw,
+                                                  double& C, double& dHdT, double& dth)
 {
     double lo = -273.0, hi = 1.0e4;
-    double T = (T0 > lo && T0 < hi) ? T0 : 0.0;
+    if (!(T > lo && T < hi)) T = 0.0;
     for (int it = 0; it < 200; ++it) {
-        double dth;
-        double thw = sfcc_theta(lc, T, dth);
-        double C = fma(dC, thw, lc[LC_CBS]);
+        thw = sfcc_theta(lc, T, dth);
+        C = fma(dC, thw, lc[LC_CBS]);
         double r = (T * C + L * thw) - H;
-        double dHdT = C + dth * (L + T * dC);
+        dHdT = C + dth * (L + T * dC);                 // heat_methods.jl:105
         if (r > 0.0) hi = T; else lo = T;
-        double Tn = T - r / dHdT;
-        if (!(Tn > lo && Tn < hi) || !isfinite(Tn)) Tn = 0.5 * (lo + hi);
-        bool done = fabs(Tn - T) <= 1e-15 * fmax(1.0, fabs(Tn));
+        double Tn = EXACT ? T - r / dHdT : fma(-r, rcp_fast(dHdT), T);
+        bool safe = (Tn >= lo && Tn <= hi);            // inclusive: a converged step may land on the bracket end (NaN -> false)
+        if (!safe) Tn = 0.5 * (lo + hi);
+        double dT = Tn - T;
+        bool done = safe && fabs(dT) <= (EXACT ? 1e-15 : 1e-9) * fmax(1.0, fabs(Tn));
         T = Tn;
-        if (done) break;
+        if (done) {
+            if (EXACT) {
+                thw = sfcc_theta(lc, T, dth);
+                C = fma(dC, thw, lc[LC_CBS]);
+                dHdT = C + dth * (L + T * dC);
+            } else {
+                thw = fma(dth, dT, thw);
+                C = fma(dC, thw, lc[LC_CBS]);
+            }
+            break;
+        }
     }
-    return T;
 }
 
-// H -> (T, θw, C, dHdT, dθw/dT, kc) for one cell.
-template <bool ALL_FW>
+// H -> (T, θw, C, dHdT, dθw/dT, kc) for one cell.  `lidx` caches the LUT interval of this cell between steps.
+template <bool ALL_FW, bool EXACT = true>
 __device__ __forceinline__ void freezethaw_cell(const Dev& P, const double* lc, double H, double dC, double dK,
-                                                double& T, double& thw, double& C, double& dHdT, double& dth, double& kc)
+                                                double& T, double& thw, double& C, double& dHdT, double& dth, double& kc,
+                                                int* lidx = nullptr)
 {
     int kind = ALL_FW ? 0 : reinterpret_cast<const int*>(lc + LC_KIND)[0];
     if (ALL_FW || (kind & 0xff) == 0) {
         // FreeWater: heat_conduction.jl:18-57 (θw = clamp(H/Lθ,0,1) θtot; T piecewise; ∂H∂T = 1e8 at T == 0)
         double x = H * lc[LC_INVLTHTOT];
-        double xc = fmin(fmax(x, 0.0), 1.0);
+        double xc = sel_min(sel_max(x, 0.0), 1.0);
         thw = xc * lc[LC_THTOT];
         C = fma(dC, thw, lc[LC_CB]);
         double invC = rcp_fast(C);
@@ -116,13 +132,15 @@ __device__ __forceinline__ void freezethaw_cell(const Dev& P, const double* lc, 
         if (solver == 0) {
             int off = reinterpret_cast<const int*>(lc + LC_TABOFF)[0];
             const int* tl = reinterpret_cast<const int*>(lc + LC_TABLEN);
-            T = lut_eval(P.lutH + off, P.lutT + off, tl[0], tl[1], H);
+            int tmp = 0;
+            T = lidx ? lut_eval_cached(P.lutH + off, P.lutT + off, tl[0], tl[1], H, *lidx)
+                     : lut_eval_cached(P.lutH + off, P.lutT + off, tl[0], tl[1], H, tmp);
+            thw = sfcc_theta(lc, T, dth);
+            C = fma(dC, thw, lc[LC_CBS]);
+            dHdT = C + dth * (P.L + T * dC);   // heat_methods.jl:105
         } else {
-            T = sfcc_newton(lc, P.L, dC, H, T);
+            sfcc_newton_solve<EXACT>(lc, P.L, dC, H, T, thw, C, dHdT, dth);
         }
-        thw = sfcc_theta(lc, T, dth);
-        C = fma(dC, thw, lc[LC_CBS]);
-        dHdT = C + dth * (P.L + T * dC);   // heat_methods.jl:105
     }
     double s = fma(dK, thw, lc[LC_KB]);
     kc = s * s;
@@ -214,11 +232,13 @@ __global__ void __launch_bounds__(128) k_heat_euler(const __grid_constant__ Dev 
         __syncwarp();
 
         double H[CPL], T[CPL];
+        int lidx[CPL];
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
             int i = lane * CPL + j;
             H[j] = (i < N) ? P.u[(size_t)i * M + col] : 0.0;
             T[j] = H[j] / P.ch_w;   // Newton seed (soil_heat.jl:127)
+            lidx[j] = 0;
         }
         double t = DIAG ? t_target : P.t[col];
         double dt = P.dt[col];
@@ -239,7 +259,7 @@ __global__ void __launch_bounds__(128) k_heat_euler(const __grid_constant__ Dev 
             double kc[CPL], thw[CPL], C[CPL], dHdT[CPL], dth[CPL];
 #pragma unroll
             for (int j = 0; j < CPL; ++j)
-                freezethaw_cell<FAST>(P, lcw + loff[j], H[j], dC, dK, T[j], thw[j], C[j], dHdT[j], dth[j], kc[j]);
+                freezethaw_cell<FAST, DIAG>(P, lcw + loff[j], H[j], dC, dK, T[j], thw[j], C[j], dHdT[j], dth[j], kc[j], &lidx[j]);
 
             // ---- stage B/C: edge fluxes (upper edge of every local cell)
             double Tup = __shfl_up_sync(FULL, T[CPL - 1], 1);
@@ -311,7 +331,11 @@ __global__ void __launch_bounds__(128) k_heat_euler(const __grid_constant__ Dev 
             }
             maxabs = warp_max(maxabs);
 #pragma unroll
-            for (int j = 0; j < CPL; ++j) H[j] = fma(dt, dH[j], H[j]);   // u += dt*du (basic_solvers.jl:66)
+            for (int j = 0; j < CPL; ++j) {
+                double inc = dt * dH[j];
+                H[j] += inc;                                              // u += dt*du (basic_solvers.jl:66)
+                if (!FAST) T[j] = fma(inc, rcp_fast(dHdT[j]), T[j]);      // first-order predictor = next Newton seed
+            }
             t = t + dt;
             ++nsteps;
             // ---- next dt: timestep() from the OLD du (basic_solvers.jl:76-77), then saveat! clip

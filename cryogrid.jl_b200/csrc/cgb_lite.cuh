@@ -36,19 +36,18 @@ __device__ __forceinline__ void lite_cell(const Dev& P, const double* lc, double
         c.dHdT = (T == 0.0) ? 1e8 : C;
     } else {
         int solver = (kind >> 8) & 0xff;
-        double T = Tguess;
+        double T = Tguess, thw, C, dHdT, dth;
         if (solver == 0) {
             int off = reinterpret_cast<const int*>(lc + LC_TABOFF)[0];
             const int* tl = reinterpret_cast<const int*>(lc + LC_TABLEN);
             T = lut_eval(P.lutH + off, P.lutT + off, tl[0], tl[1], H);
+            thw = sfcc_theta(lc, T, dth);
+            C = fma(dC, thw, lc[LC_CBS]);
+            dHdT = C + dth * (P.L + T * dC);
         } else {
-            T = sfcc_newton(lc, P.L, dC, H, T);
+            sfcc_newton_solve<true>(lc, P.L, dC, H, T, thw, C, dHdT, dth);
         }
-        double dth;
-        double thw = sfcc_theta(lc, T, dth);
-        double C = fma(dC, thw, lc[LC_CBS]);
-        c.T = T; c.thw = thw; c.C = C; c.dth = dth;
-        c.dHdT = C + dth * (P.L + T * dC);
+        c.T = T; c.thw = thw; c.C = C; c.dth = dth; c.dHdT = dHdT;
     }
     double s = fma(dK, c.thw, lc[LC_KB]);
     c.kc = s * s;

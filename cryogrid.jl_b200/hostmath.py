@@ -138,7 +138,7 @@ def sfcc_newton(fc, tp, por, sat, org, H, T0):
         else:
             lo = T
         Tn = T - r / dHdT
-        if not (lo < Tn < hi) or not np.isfinite(Tn):
+        if not (lo <= Tn <= hi):
             Tn = 0.5 * (lo + hi)
         done = abs(Tn - T) <= 1e-15 * max(1.0, abs(Tn))
         T = Tn

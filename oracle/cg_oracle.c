@@ -253,7 +253,7 @@ double cg_sfcc_newton(const cg_freezecurve* fc, const cg_thermal* tp, double por
         double r = sfcc_enthalpy(fc, tp, por, sat, org, T, &dHdT, NULL) - H;
         if (r > 0.0) hi = T; else lo = T;
         double Tn = T - r / dHdT;
-        if (!(Tn > lo && Tn < hi) || !isfinite(Tn)) Tn = 0.5 * (lo + hi);
+        if (!(Tn >= lo && Tn <= hi)) Tn = 0.5 * (lo + hi); /* inclusive: a converged step may land on the bracket end */
         if (fabs(Tn - T) <= 1e-15 * fmax(1.0, fabs(Tn))) { T = Tn; break; }
         T = Tn;
     }
