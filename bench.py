@@ -230,20 +230,26 @@ def main():
     # ---- e2e: public API with host buffers (H2D of u0 + D2H of the daily saved T inside the timed region)
     e2e = None
     if not args.no_e2e:
+        # same simulated window as the first timed step: start from the state after the spin-up (held in pinned HOST
+        # memory), upload it, integrate D days with daily saves of T, and bring every save back to pinned host memory
         nsave = int(D)
-        prob = cg.CryoGridProblem(tile, H0, (0.0, nsave * DAY), saveat=DAY, savevars=("T",))
-        e2e_steps = min(K, 2)
-        eng2 = cg.Engine(tile, stepper="euler", device=local)
-        pinned_out = torch.empty((nsave + 1, 1, N, M), dtype=torch.float64, pin_memory=True).numpy()
+        t_w = W * D * DAY
+        eng_w = cg.Engine(tile, stepper="euler", device=local)
+        eng_w.set_state(H0, 0.0)
+        eng_w.advance_to(t_w)
         pinned_u0 = torch.empty((N, M), dtype=torch.float64, pin_memory=True).numpy()
-        pinned_u0[:] = H0
-        prob.u0 = pinned_u0
-        cg.solve(prob, cg.CGEuler(), engine=eng2, out=pinned_out)        # warm-up (allocates the device staging buffers)
+        pinned_u0[:] = eng_w.get_state()
+        eng_w.close()
+        pinned_out = torch.empty((nsave + 1, 1, N, M), dtype=torch.float64, pin_memory=True).numpy()
+        prob = cg.CryoGridProblem(tile, pinned_u0, (t_w, t_w + nsave * DAY), saveat=DAY, savevars=("T",))
+        e2e_steps = max(1, min(K, 3))
+        eng2 = cg.Engine(tile, stepper="euler", device=local)
+        cg.solve(prob, cg.CGEuler(), engine=eng2, out=pinned_out, return_state=False)   # warm-up (allocates the staging buffers)
         barrier()
         t0 = time.perf_counter()
         cs2 = 0
         for _ in range(e2e_steps):
-            sol = cg.solve(prob, cg.CGEuler(), engine=eng2, out=pinned_out)
+            sol = cg.solve(prob, cg.CGEuler(), engine=eng2, out=pinned_out, return_state=False)
             cs2 += sol.stats["cell_steps"]
         barrier()
         el = time.perf_counter() - t0
@@ -252,9 +258,10 @@ def main():
             a = te.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
             b = te.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
             el, cs2 = float(a[0]), float(b[1])
-        e2e = {"value": cs2 / el, "unit": "cell-steps/s", "h2d_bytes_per_step": int(H0.nbytes),
-               "d2h_bytes_per_step": int((nsave + 1) * N * M * 8), "steps": e2e_steps,
-               "note": "solve(CryoGridProblem(saveat=1 day, savevars=T)) from host u0; saved T copied back to host"}
+        e2e = {"value": cs2 / el, "unit": "cell-steps/s", "h2d_bytes_per_step": int(pinned_u0.nbytes),
+               "d2h_bytes_per_step": int((nsave + 1) * N * M * 8), "steps": e2e_steps, "ms_per_step": 1e3 * el / e2e_steps,
+               "note": "solve(CryoGridProblem(saveat=1 day, savevars=T)) on the first timed window, u0 uploaded from pinned host "
+                       "memory, every saved T copied back to pinned host memory (overlapped on a second stream)"}
         eng2.close()
 
     cpu = None

@@ -37,7 +37,7 @@ class CryoGridSolution:
             prob, t, u, saved, stats, status, steps, retcode
 
 
-def solve(prob, alg=None, dt=None, dtmax=None, dtmin=1.0, device=0, engine=None, out=None):
+def solve(prob, alg=None, dt=None, dtmax=None, dtmin=1.0, device=0, engine=None, out=None, return_state=True):
     """solve(prob, alg; dt, dtmax, dtmin).  Saved variables come back as [nsave, nvars, N, M]."""
     alg = alg or CGEuler()
     lite = isinstance(alg, LiteImplicitEuler)
@@ -60,7 +60,7 @@ def solve(prob, alg=None, dt=None, dtmax=None, dtmin=1.0, device=0, engine=None,
         eng.solve_saveat(saves[first:], savevars, out=out[first:])
     if saves.size == 0 or saves[-1] < prob.tspan[1]:
         eng.advance_to(prob.tspan[1])
-    u, t, _ = eng.get_state(with_time=True)
+    u = eng.get_state() if return_state else None      # sol.u[end]; skip when only the saved outputs are consumed
     status, steps = eng.status()
     retcode = "Success" if not status.any() else ("MaxIters" if (status & 1).any() and not (status & ~1).any() else "Failure")
     sol = CryoGridSolution(prob, saves, u, out, eng.stats(), status, steps, retcode)
