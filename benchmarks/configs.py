@@ -100,6 +100,15 @@ def main():
         eng = cg.Engine(tile); eng.set_state(H0, 0.0); eng.advance_to(1 * DAY)
         r = timed(eng, [DAY * d for d in range(2, 6)]); r.update(config="cfg4' SFCC DallAmico presolver LUT, N=218, 4 days", columns=M)
         out.append(r); eng.close()
+        # PainterKarra with van Genuchten n = 2 (the value examples/heat_sfcc_constantbc.jl uses): rsqrt fast path
+        tile = common.sfcc_tile(ncolumns=M, kind="painterkarra", solver="lut", alpha=1.0, n=2.0, grid=cg.DefaultGrid_5cm,
+                                top=cg.PeriodicBC(cg.Dirichlet, common.YEAR, 18.0, 0.0, -10.0), bottom=cg.GeothermalHeatFlux(0.053),
+                                temp=cg.SamoylovDefault_tempprofile)
+        tile.top_offset = rng.normal(0.0, 2.0, M)
+        H0 = cg.initialcondition(tile)
+        eng = cg.Engine(tile); eng.set_state(H0, 0.0); eng.advance_to(1 * DAY)
+        r = timed(eng, [DAY * d for d in range(2, 6)]); r.update(config="cfg4'' SFCC PainterKarra n=2 presolver LUT, N=218, 4 days", columns=M)
+        out.append(r); eng.close()
     if want("cfg5"):
         M = int(100000 * args.scale)
         rng = np.random.default_rng(5)

@@ -291,11 +291,35 @@ static int finalize(cgb_handle* h)
             }
         }
     }
-    double *p_lh, *p_lt; int *p_off, *p_len, *p_ext, *p_map = nullptr;
-    rc |= dev_upload(h, &p_lh, allH); rc |= dev_upload(h, &p_lt, allT);
+    // segment slopes and the bucket acceleration index of every table (see lut_eval_bucket)
+    std::vector<double> allS(allH.size(), 0.0);
+    std::vector<int2> allB;
+    std::vector<int> boff(off.size(), 0), nit(off.size(), 1);
+    for (auto& kv : h->tables) {
+        const std::vector<double>& H = kv.second.H; const std::vector<double>& T = kv.second.T;
+        int nk = (int)H.size(), o = off[kv.first];
+        for (int i = 0; i + 1 < nk; ++i) allS[o + i] = (T[i + 1] - T[i]) / (H[i + 1] - H[i]);
+        allS[o + nk - 1] = allS[o + nk - 2];
+        boff[kv.first] = (int)allB.size();
+        double hmin = H[0], bw = (H[nk - 1] - H[0]) / LUT_NB;
+        int maxr = 1;
+        auto last_le = [&](double x) { return (int)(std::upper_bound(H.begin(), H.end(), x) - H.begin()) - 1; };
+        for (int b = 0; b < LUT_NB; ++b) {
+            int lo = std::max(last_le(hmin + b * bw) - 1, 0), hi = std::min(last_le(hmin + (b + 1) * bw) + 1, nk - 2);
+            lo = std::min(lo, nk - 2); hi = std::max(hi, lo);
+            allB.push_back(make_int2(lo, hi));
+            maxr = std::max(maxr, hi - lo + 1);
+        }
+        int it = 0; while ((1 << it) < maxr) ++it;
+        nit[kv.first] = it + 1;
+    }
+    double *p_lh, *p_lt, *p_ls; int2* p_lb; int *p_off, *p_len, *p_ext, *p_boff, *p_nit, *p_map = nullptr;
+    rc |= dev_upload(h, &p_lh, allH); rc |= dev_upload(h, &p_lt, allT); rc |= dev_upload(h, &p_ls, allS); rc |= dev_upload(h, &p_lb, allB);
     rc |= dev_upload(h, &p_off, off); rc |= dev_upload(h, &p_len, len); rc |= dev_upload(h, &p_ext, ext);
+    rc |= dev_upload(h, &p_boff, boff); rc |= dev_upload(h, &p_nit, nit);
     if (!h->table_map.empty()) rc |= dev_upload(h, &p_map, h->table_map);
-    d.lutH = p_lh; d.lutT = p_lt; d.lut_off = p_off; d.lut_len = p_len; d.lut_extrap = p_ext; d.table_map = p_map;
+    d.lutH = p_lh; d.lutT = p_lt; d.lutS = p_ls; d.lutB = p_lb; d.lut_off = p_off; d.lut_len = p_len; d.lut_extrap = p_ext;
+    d.lut_boff = p_boff; d.lut_nit = p_nit; d.table_map = p_map;
     // per (layer, column) parameters
     auto up_cl = [&](const char* name, const double** dst) {
         double* p; std::vector<double> v = expand(h, h->params[name], CGB_PER_COLUMN_LAYER);
@@ -459,10 +483,10 @@ static bool all_freewater(const cgb_handle* h)
     return true;
 }
 
-template <int CPL, bool FAST, bool DIAG>
+template <int CPL, int MODE, bool DIAG>
 static int launch_euler_t(cgb_handle* h, double t_target, const Diag& D)
 {
-    auto kern = k_heat_euler<CPL, FAST, DIAG>;
+    auto kern = k_heat_euler<CPL, MODE, DIAG>;
     size_t smem = (size_t)(5 * CPL * 32 + 4 * h->nl * LC_STRIDE) * sizeof(double);
     static int blocks_per_sm = 0;   // per instantiation
     if (blocks_per_sm == 0) {
@@ -479,21 +503,21 @@ static int launch_euler_t(cgb_handle* h, double t_target, const Diag& D)
     return CGB_OK;
 }
 
-template <bool FAST, bool DIAG>
+template <int MODE, bool DIAG>
 static int launch_euler_c(cgb_handle* h, double t_target, const Diag& D)
 {
     int cpl = (h->N + 31) / 32;
     switch (cpl) {
-    case 1: return launch_euler_t<1, FAST, DIAG>(h, t_target, D);
-    case 2: return launch_euler_t<2, FAST, DIAG>(h, t_target, D);
-    case 3: case 4: return launch_euler_t<4, FAST, DIAG>(h, t_target, D);
-    case 5: case 6: return launch_euler_t<6, FAST, DIAG>(h, t_target, D);
-    case 7: return launch_euler_t<7, FAST, DIAG>(h, t_target, D);
-    case 8: return launch_euler_t<8, FAST, DIAG>(h, t_target, D);
-    case 9: return launch_euler_t<9, FAST, DIAG>(h, t_target, D);
-    case 10: return launch_euler_t<10, FAST, DIAG>(h, t_target, D);
-    case 11: case 12: return launch_euler_t<12, FAST, DIAG>(h, t_target, D);
-    default: return launch_euler_t<16, FAST, DIAG>(h, t_target, D);
+    case 1: return launch_euler_t<1, MODE, DIAG>(h, t_target, D);
+    case 2: return launch_euler_t<2, MODE, DIAG>(h, t_target, D);
+    case 3: case 4: return launch_euler_t<4, MODE, DIAG>(h, t_target, D);
+    case 5: case 6: return launch_euler_t<6, MODE, DIAG>(h, t_target, D);
+    case 7: return launch_euler_t<7, MODE, DIAG>(h, t_target, D);
+    case 8: return launch_euler_t<8, MODE, DIAG>(h, t_target, D);
+    case 9: return launch_euler_t<9, MODE, DIAG>(h, t_target, D);
+    case 10: return launch_euler_t<10, MODE, DIAG>(h, t_target, D);
+    case 11: case 12: return launch_euler_t<12, MODE, DIAG>(h, t_target, D);
+    default: return launch_euler_t<16, MODE, DIAG>(h, t_target, D);
     }
 }
 
@@ -592,13 +616,24 @@ static int launch_advance_inner(cgb_handle* h, double t_target)
         return lite_warp_launch(h, t_target);
     }
     bool fast = all_freewater(h) && h->cfg.limiter == CGB_LIMITER_MAXDELTA && h->fast_ok;
-    return fast ? launch_fast(h, t_target) : launch_euler_c<false, false>(h, t_target, D);
+    if (fast) return launch_fast(h, t_target);
+    // solver mode of the general kernel: 1 = every layer SFCC + LUT, 2 = every layer SFCC + Newton, 3 = every layer FreeWater, 0 = mixed
+    bool all_lut = true, all_newton = true;
+    for (int l = 0; l < h->nl; ++l) {
+        bool sf = h->fc_kind[l] != CGB_FC_FREEWATER;
+        all_lut &= sf && h->fc_solver[l] == CGB_SOLVER_LUT;
+        all_newton &= sf && h->fc_solver[l] == CGB_SOLVER_NEWTON;
+    }
+    if (all_lut) return launch_euler_c<1, false>(h, t_target, D);
+    if (all_newton) return launch_euler_c<2, false>(h, t_target, D);
+    if (all_freewater(h)) return launch_euler_c<3, false>(h, t_target, D);
+    return launch_euler_c<0, false>(h, t_target, D);
 }
 
 static int launch_diag(cgb_handle* h, double t, const Diag& D)
 {
     if (h->cfg.stepper == CGB_STEPPER_LITE_IMPLICIT) return lite_launch(h, t, true, D);
-    return launch_euler_c<false, true>(h, t, D);
+    return launch_euler_c<0, true>(h, t, D);
 }
 
 extern "C" int cgb_advance_to(cgb_handle* h, double t_target)

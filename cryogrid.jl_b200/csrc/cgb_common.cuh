@@ -9,7 +9,8 @@ namespace cgb {
 constexpr unsigned FULL = 0xffffffffu;
 
 // per-(column, layer) derived constants staged in shared memory (one block per warp)
-constexpr int LC_STRIDE = 20;
+constexpr int LC_STRIDE = 24;
+constexpr int LUT_NB = 1024;   // uniform H-buckets per presolver table (acceleration index built on the host)
 enum LayerConst {
     LC_THWI = 0,   // θwi = por*sat                        (Soils/para/simple.jl:19,87)
     LC_LTH,        // L*θwi                                 (heat_conduction.jl:40)
@@ -27,9 +28,13 @@ enum LayerConst {
     LC_CFAC,       // β Lsl/(g T*)
     LC_CBS,        // sfccheatcap at θw = 0 (with the (1-θsat) quirk, soil_heat.jl:13-14)
     LC_KIND,       // int: freeze-curve kind | solver<<8
-    LC_TABOFF,     // int: LUT offset
-    LC_TABLEN,     // int: LUT length | extrap<<24
+    LC_TABOFF,     // int2: LUT knot offset, LUT length
+    LC_TABLEN,     // int2: extrapolation mode, bisection iterations
     LC_SAT,        // θwi/por
+    LC_BOFF,       // int2: bucket-array offset, unused
+    LC_HMIN,       // first knot
+    LC_HMAX,       // last knot
+    LC_INVBW,      // LUT_NB / (Hmax - Hmin)
     LC_SPARE
 };
 
@@ -59,8 +64,9 @@ struct Dev {
     const double *por, *sat, *org;                               // [n_layers*M]
     const double *vg_alpha, *vg_n, *theta_res, *Tm, *beta, *omega; // [n_layers*M]
     const int* table_map;     // [n_layers*M] or nullptr
-    const double* lutH; const double* lutT;
-    const int* lut_off; const int* lut_len; const int* lut_extrap;
+    const double* lutH; const double* lutT; const double* lutS;   // knots H, T and segment slopes dT/dH (concatenated tables)
+    const int2* lutB;         // per table LUT_NB buckets: [lo, hi] range of candidate segments (concatenated)
+    const int* lut_off; const int* lut_len; const int* lut_extrap; const int* lut_boff; const int* lut_nit;
     // thermal properties
     double sk_w, sk_i, sk_a, sk_m, sk_o;   // sqrt(kh_*)
     double ch_w, ch_i, ch_a, ch_m, ch_o, L;
@@ -127,6 +133,19 @@ __device__ __forceinline__ double rcp_fast3(double a)
     return fma(y, p, y);
 }
 
+// 1/sqrt(a) from MUFU.RSQ64H + two Newton steps (a > 0, normal range).
+__device__ __forceinline__ double rsqrt_fast(double a)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double h = 0.5 * y;
+    double e = fma(-a * y, y, 1.0);
+    y = fma(h, e, y);
+    h = 0.5 * y;
+    e = fma(-a * y, y, 1.0);
+    return fma(h, e, y);
+}
+
 __device__ __forceinline__ double rcp_raw(double a)
 {
     double y;
@@ -181,6 +200,25 @@ __device__ __forceinline__ double lut_eval(const double* __restrict__ Hk, const 
     return lerp_table(Hk, Tk, nk, H);
 }
 
+// Presolver interpolant through the bucket index: one bucket load narrows the segment to <= ~16 candidates, then a
+// fixed-trip, branch-free bisection (no warp divergence), then T = T_i + (H - H_i) * slope_i.  Linear extrapolation
+// uses the end segments; flat extrapolation clamps H to the knot range first.
+__device__ __forceinline__ double lut_eval_bucket(const double* __restrict__ Hk, const double* __restrict__ Tk, const double* __restrict__ Sk,
+                                                  const int2* __restrict__ B, double hmin, double hmax, double invbw, int extrap, int nit, double H)
+{
+    if (extrap == 0) H = sel_min(sel_max(H, hmin), hmax);
+    double fb = sel_min(sel_max((H - hmin) * invbw, 0.0), (double)(LUT_NB - 1));
+    int2 r = __ldg(B + (int)fb);
+    int lo = r.x, hi = r.y;
+    for (int k = 0; k < nit; ++k) {
+        int mid = (lo + hi + 1) >> 1;
+        bool p = __ldg(Hk + mid) <= H;
+        lo = p ? mid : lo;
+        hi = p ? hi : mid - 1;
+    }
+    return fma(H - __ldg(Hk + lo), __ldg(Sk + lo), __ldg(Tk + lo));
+}
+
 // LUT evaluation with a cached knot interval (H moves slowly between steps): probe the cached interval first, fall back
 // to the binary search.  Same result as lut_eval.
 __device__ __forceinline__ double lut_eval_cached(const double* __restrict__ Hk, const double* __restrict__ Tk, int nk, int extrap, double H, int& idx)
@@ -213,6 +251,12 @@ __device__ __forceinline__ double vg_theta(double psi, double thsat, double thre
     if (psi <= 0.0) {
         double x = fabs(-alpha * psi);
         double d = thsat - thres;
+        if (n == 2.0) {
+            // m = 1/2: θ = θres + Δθ (1+x²)^(-1/2), dθ/dψ = Δθ α x (1+x²)^(-3/2)  -- no transcendental at all
+            double rs = rsqrt_fast(fma(x, x, 1.0));
+            dth = d * alpha * x * (rs * rs * rs);
+            return fma(d, rs, thres);
+        }
         if (x > 0.0) {
             double xn = exp(n * log(x));
             double base = 1.0 + xn;

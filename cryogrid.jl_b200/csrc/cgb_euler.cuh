@@ -59,9 +59,12 @@ __device__ __forceinline__ void layer_consts(const Dev& P, long long col, int l,
         c[LC_CBS] = P.ch_i * thwi + P.ch_a * (por - thwi) + P.ch_m * (thm * (1.0 - por)) + P.ch_o * (tho * (1.0 - por));
         if (((kind >> 8) & 0xff) == 0) {
             int id = P.table_map ? P.table_map[ix] : l;
-            to[0] = P.lut_off[id];
-            tl[0] = P.lut_len[id];
-            tl[1] = P.lut_extrap[id];
+            int off = P.lut_off[id], nk = P.lut_len[id];
+            to[0] = off; to[1] = nk;
+            tl[0] = P.lut_extrap[id]; tl[1] = P.lut_nit[id];
+            reinterpret_cast<int*>(c + LC_BOFF)[0] = P.lut_boff[id];
+            double hmin = P.lutH[off], hmax = P.lutH[off + nk - 1];
+            c[LC_HMIN] = hmin; c[LC_HMAX] = hmax; c[LC_INVBW] = (double)LUT_NB / (hmax - hmin);
         }
     }
 }
@@ -107,14 +110,23 @@ __device__ __forceinline__ void sfcc_newton_solve(const double* lc, double L, do
     }
 }
 
-// H -> (T, θw, C, dHdT, dθw/dT, kc) for one cell.  `lidx` caches the LUT interval of this cell between steps.
-template <bool ALL_FW, bool EXACT = true>
-__device__ __forceinline__ void freezethaw_cell(const Dev& P, const double* lc, double H, double dC, double dK,
-                                                double& T, double& thw, double& C, double& dHdT, double& dth, double& kc,
-                                                int* lidx = nullptr)
+__device__ __forceinline__ double lut_T(const Dev& P, const double* lc, double H)
 {
-    int kind = ALL_FW ? 0 : reinterpret_cast<const int*>(lc + LC_KIND)[0];
-    if (ALL_FW || (kind & 0xff) == 0) {
+    const int* to = reinterpret_cast<const int*>(lc + LC_TABOFF);
+    const int* tl = reinterpret_cast<const int*>(lc + LC_TABLEN);
+    int off = to[0], boff = reinterpret_cast<const int*>(lc + LC_BOFF)[0];
+    return lut_eval_bucket(P.lutH + off, P.lutT + off, P.lutS + off, P.lutB + boff, lc[LC_HMIN], lc[LC_HMAX], lc[LC_INVBW], tl[0], tl[1], H);
+}
+
+// H -> (T, θw, C, dHdT, dθw/dT, kc) for one cell.
+// MODE: 0 = freeze curve / solver read from the layer constants (generic), 1 = every layer is SFCC + presolver LUT,
+//       2 = every layer is SFCC + Newton, 3 = every layer is FreeWater.  EXACT: fully converged Newton (diagnostics).
+template <int MODE, bool EXACT>
+__device__ __forceinline__ void freezethaw_body(const Dev& P, const double* lc, double H, double dC, double dK,
+                                                double& T, double& thw, double& C, double& dHdT, double& dth, double& kc)
+{
+    int kind = (MODE == 0) ? reinterpret_cast<const int*>(lc + LC_KIND)[0] : (MODE == 3 ? 0 : (MODE == 1 ? 1 : (1 | (1 << 8))));
+    if ((kind & 0xff) == 0) {
         // FreeWater: heat_conduction.jl:18-57 (θw = clamp(H/Lθ,0,1) θtot; T piecewise; ∂H∂T = 1e8 at T == 0)
         double x = H * lc[LC_INVLTHTOT];
         double xc = sel_min(sel_max(x, 0.0), 1.0);
@@ -126,24 +138,34 @@ __device__ __forceinline__ void freezethaw_cell(const Dev& P, const double* lc, 
         T = num * invC;
         dHdT = (T == 0.0) ? 1e8 : C;
         dth = 0.0;
+    } else if (((kind >> 8) & 0xff) == 0) {
+        // SFCC + presolver: soil_heat.jl:116-140 -- T from the table, then θw, ∂θw∂T at T
+        T = lut_T(P, lc, H);
+        thw = sfcc_theta(lc, T, dth);
+        C = fma(dC, thw, lc[LC_CBS]);
+        dHdT = C + dth * (P.L + T * dC);   // heat_methods.jl:105
     } else {
-        // SFCC: soil_heat.jl:116-140 -- T from the presolver table (or Newton), then θw, ∂θw∂T at T.
-        int solver = (kind >> 8) & 0xff;
-        if (solver == 0) {
-            int off = reinterpret_cast<const int*>(lc + LC_TABOFF)[0];
-            const int* tl = reinterpret_cast<const int*>(lc + LC_TABLEN);
-            int tmp = 0;
-            T = lidx ? lut_eval_cached(P.lutH + off, P.lutT + off, tl[0], tl[1], H, *lidx)
-                     : lut_eval_cached(P.lutH + off, P.lutT + off, tl[0], tl[1], H, tmp);
-            thw = sfcc_theta(lc, T, dth);
-            C = fma(dC, thw, lc[LC_CBS]);
-            dHdT = C + dth * (P.L + T * dC);   // heat_methods.jl:105
-        } else {
-            sfcc_newton_solve<EXACT>(lc, P.L, dC, H, T, thw, C, dHdT, dth);
-        }
+        sfcc_newton_solve<EXACT>(lc, P.L, dC, H, T, thw, C, dHdT, dth);
     }
     double s = fma(dK, thw, lc[LC_KB]);
     kc = s * s;
+}
+
+// The generic (MODE 0) body carries all three branches; it is kept out of line so that the CPL-times unrolled step
+// loop stays inside the instruction cache (the inlined version was 170 KB of SASS and stalled on instruction fetch).
+template <bool EXACT>
+__device__ __noinline__ void freezethaw_generic(const Dev& P, const double* lc, double H, double dC, double dK,
+                                                double& T, double& thw, double& C, double& dHdT, double& dth, double& kc)
+{
+    freezethaw_body<0, EXACT>(P, lc, H, dC, dK, T, thw, C, dHdT, dth, kc);
+}
+
+template <int MODE, bool EXACT = true>
+__device__ __forceinline__ void freezethaw_cell(const Dev& P, const double* lc, double H, double dC, double dK,
+                                                double& T, double& thw, double& C, double& dHdT, double& dth, double& kc)
+{
+    if (MODE == 0) freezethaw_generic<EXACT>(P, lc, H, dC, dK, T, thw, C, dHdT, dth, kc);
+    else freezethaw_body<MODE, EXACT>(P, lc, H, dC, dK, T, thw, C, dHdT, dth, kc);
 }
 
 // Warp-uniform forcing evaluation with a cursor into the table (t only moves forward).
@@ -180,7 +202,7 @@ __device__ __forceinline__ double forcing_eval(const Forcing& F, ForcingCursor& 
 }
 
 // -------------------------------------------------------------------------------------------------
-template <int CPL, bool FAST, bool DIAG>
+template <int CPL, int MODE, bool DIAG>
 __global__ void __launch_bounds__(128) k_heat_euler(const __grid_constant__ Dev P, double t_target, Diag D)
 {
     extern __shared__ double smem[];
@@ -232,13 +254,11 @@ __global__ void __launch_bounds__(128) k_heat_euler(const __grid_constant__ Dev 
         __syncwarp();
 
         double H[CPL], T[CPL];
-        int lidx[CPL];
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
             int i = lane * CPL + j;
             H[j] = (i < N) ? P.u[(size_t)i * M + col] : 0.0;
             T[j] = H[j] / P.ch_w;   // Newton seed (soil_heat.jl:127)
-            lidx[j] = 0;
         }
         double t = DIAG ? t_target : P.t[col];
         double dt = P.dt[col];
@@ -259,7 +279,7 @@ __global__ void __launch_bounds__(128) k_heat_euler(const __grid_constant__ Dev 
             double kc[CPL], thw[CPL], C[CPL], dHdT[CPL], dth[CPL];
 #pragma unroll
             for (int j = 0; j < CPL; ++j)
-                freezethaw_cell<FAST, DIAG>(P, lcw + loff[j], H[j], dC, dK, T[j], thw[j], C[j], dHdT[j], dth[j], kc[j], &lidx[j]);
+                freezethaw_cell<MODE, DIAG>(P, lcw + loff[j], H[j], dC, dK, T[j], thw[j], C[j], dHdT[j], dth[j], kc[j]);
 
             // ---- stage B/C: edge fluxes (upper edge of every local cell)
             double Tup = __shfl_up_sync(FULL, T[CPL - 1], 1);
@@ -298,7 +318,7 @@ __global__ void __launch_bounds__(128) k_heat_euler(const __grid_constant__ Dev 
                 int s = j * 32 + lane;
                 dH[j] = (je[j] - jlow) * sInvDk[s];
                 maxabs = fmax(maxabs, fabs(dH[j]));
-                if (!FAST && P.limiter == 1) {
+                if (P.limiter == 1) {
                     double dx = sDk[s];
                     double v = dHdT[j] * rcp_fast(kc[j]);
                     double c = P.courant * v * (dx * dx);
@@ -334,14 +354,14 @@ __global__ void __launch_bounds__(128) k_heat_euler(const __grid_constant__ Dev 
             for (int j = 0; j < CPL; ++j) {
                 double inc = dt * dH[j];
                 H[j] += inc;                                              // u += dt*du (basic_solvers.jl:66)
-                if (!FAST) T[j] = fma(inc, rcp_fast(dHdT[j]), T[j]);      // first-order predictor = next Newton seed
+                if (MODE == 0 || MODE == 2) T[j] = fma(inc, rcp_fast(dHdT[j]), T[j]);   // first-order predictor = next Newton seed
             }
             t = t + dt;
             ++nsteps;
             // ---- next dt: timestep() from the OLD du (basic_solvers.jl:76-77), then saveat! clip
             double lim = P.maxdelta / maxabs;                             // = min_i |Δmax/dH_i| (steplimiters.jl:15-18)
             if (!isfinite(lim)) lim = INFINITY;
-            if (!FAST && P.limiter == 1) {
+            if (P.limiter == 1) {
                 mincfl = warp_min(mincfl);
                 lim = fmin(lim, mincfl);
                 if (!isfinite(lim)) lim = INFINITY;                      // heat_conduction.jl:180

@@ -38,9 +38,7 @@ __device__ __forceinline__ void lite_cell(const Dev& P, const double* lc, double
         int solver = (kind >> 8) & 0xff;
         double T = Tguess, thw, C, dHdT, dth;
         if (solver == 0) {
-            int off = reinterpret_cast<const int*>(lc + LC_TABOFF)[0];
-            const int* tl = reinterpret_cast<const int*>(lc + LC_TABLEN);
-            T = lut_eval(P.lutH + off, P.lutT + off, tl[0], tl[1], H);
+            T = lut_T(P, lc, H);
             thw = sfcc_theta(lc, T, dth);
             C = fma(dC, thw, lc[LC_CBS]);
             dHdT = C + dth * (P.L + T * dC);

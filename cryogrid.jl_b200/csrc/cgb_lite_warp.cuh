@@ -20,7 +20,7 @@
 
 namespace cgb {
 
-template <int CPL>
+template <int CPL, int MODE>
 __global__ void __launch_bounds__(128, 2) k_lite_warp(const __grid_constant__ Dev P, double t_target)
 {
     extern __shared__ double smem[];
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(128, 2) k_lite_warp(const __grid_constant__ De
 #pragma unroll
                 for (int j = 0; j < CPL; ++j) {
                     double thw, C, dth;
-                    freezethaw_cell<false>(P, lcw + loff[j], H[j], dC, dK, T[j], thw, C, dHdT[j], dth, kc[j]);
+                    freezethaw_cell<MODE>(P, lcw + loff[j], H[j], dC, dK, T[j], thw, C, dHdT[j], dth, kc[j]);
                 }
                 // ---- kd = k_edge/dxc on the upper edge of every local cell (harmonic mean, math.jl:141)
                 double kup = __shfl_up_sync(FULL, kc[CPL - 1], 1);
@@ -233,11 +233,11 @@ __global__ void __launch_bounds__(128, 2) k_lite_warp(const __grid_constant__ De
 
 } // namespace cgb
 
-template <int CPL>
-static int lite_warp_launch_t(cgb_handle* h, double t_target)
+template <int CPL, int MODE>
+static int lite_warp_launch_m(cgb_handle* h, double t_target)
 {
     using namespace cgb;
-    auto kern = k_lite_warp<CPL>;
+    auto kern = k_lite_warp<CPL, MODE>;
     size_t smem = (size_t)(5 * CPL * 32 + 4 * h->nl * LC_STRIDE) * sizeof(double);
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
@@ -251,6 +251,14 @@ static int lite_warp_launch_t(cgb_handle* h, double t_target)
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return CGB_OK;
+}
+
+template <int CPL>
+static int lite_warp_launch_t(cgb_handle* h, double t_target)
+{
+    bool fw = true;
+    for (int l = 0; l < h->nl; ++l) fw &= h->fc_kind[l] == CGB_FC_FREEWATER;
+    return fw ? lite_warp_launch_m<CPL, 3>(h, t_target) : lite_warp_launch_m<CPL, 0>(h, t_target);
 }
 
 static int lite_warp_launch(cgb_handle* h, double t_target)
