@@ -244,6 +244,15 @@ __device__ __forceinline__ double lut_eval_cached(const double* __restrict__ Hk,
     return (1.0 - w) * __ldg(Tk + i) + w * __ldg(Tk + i + 1);
 }
 
+// x^n and (1+x^n)^-m for x > 0 through exp/log.  Out of line on purpose: two exp + two log are ~200 instructions, and the
+// callers are unrolled over the cells of a lane (and sit inside the Newton loop) -- inlined, the step loop overflows the
+// instruction cache (ncu: `no_instruction` was the second largest stall).
+__device__ __noinline__ void vg_powers(double x, double n, double m, double& xn, double& pb)
+{
+    xn = exp(n * log(x));
+    pb = exp(-m * log1p(xn));
+}
+
 // van Genuchten θ(ψ) and dθ/dψ for ψ <= 0; θsat for ψ > 0.  x^n and (1+x^n)^-m go through exp/log (x > 0, base >= 1:
 // no special cases needed), about half the cost of two pow() calls; error ~ (n |log x| + 2) ulp.
 __device__ __forceinline__ double vg_theta(double psi, double thsat, double thres, double alpha, double n, double m, double& dth)
@@ -258,9 +267,9 @@ __device__ __forceinline__ double vg_theta(double psi, double thsat, double thre
             return fma(d, rs, thres);
         }
         if (x > 0.0) {
-            double xn = exp(n * log(x));
+            double xn, pb;
+            vg_powers(x, n, m, xn, pb);
             double base = 1.0 + xn;
-            double pb = exp(-m * log1p(xn));
             dth = d * m * n * alpha * (xn * rcp_fast(x)) * (pb * rcp_fast(base));
             return fma(d, pb, thres);
         }
