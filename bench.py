@@ -279,9 +279,10 @@ def main():
                        "columns_per_gpu": M, "cells": N, "days_per_step": D, "l2_policy": "state (17 MB) is re-read from HBM/L2 once per "
                        "launch; inputs are not larger than L2 -- the kernel is register-resident and FP64-bound, see DESIGN.md",
                        "wall_s_timed_region": wall_s},
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": 19319808,
                          "peak_source": peak_src, "bytes_per_cell_step": BYTES_PER_CELL_STEP,
-                         "note": "achieved > peak is legal here: state stays in registers across the steps of a launch (temporal fusion)"},
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one bench step, profiles/r1c_ncu_k_heat_euler_fast_7_3_cubic.md",
+                         "note": "algorithmic bytes (16 B per cell-step) far exceed the DRAM traffic because the state stays in registers across the Euler steps of a launch (temporal fusion); the kernel is FP64-pipe bound (58 % busy)"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(s1["kernel_launches"] - s0["kernel_launches"]),
             "clocks": clk.summary(), "cell_steps": int(total_cs), "column_steps_per_column": (s1["column_steps"] - s0["column_steps"]) / M,
         }
