@@ -65,6 +65,8 @@ SIGNATURES = {
     "cgb_set_forcing_periodic": (C.c_int, [_P, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double]),
     "cgb_set_forcing_constant": (C.c_int, [_P, C.c_int32, C.c_double]),
     "cgb_set_state": (C.c_int, [_P, _D, C.c_double]),
+    "cgb_init_interp": (C.c_int, [_P, _D, _D, C.c_int64, C.c_int32, C.c_double]),
+    "cgb_init_steadystate": (C.c_int, [_P, _D, C.c_int32, C.c_double, C.c_int32, C.c_double, C.c_double]),
     "cgb_get_state": (C.c_int, [_P, _D, _D, _D]),
     "cgb_get_status": (C.c_int, [_P, _I32, _I64]),
     "cgb_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
@@ -73,6 +75,7 @@ SIGNATURES = {
     "cgb_synchronize": (C.c_int, [_P]),
     "cgb_get_diag": (C.c_int, [_P, C.c_char_p, C.c_double, _D]),
     "cgb_solve_saveat": (C.c_int, [_P, _D, C.c_int64, C.c_char_p, _D]),
+    "cgb_solve_saveat_select": (C.c_int, [_P, _D, C.c_int64, C.c_char_p, _I32, C.c_int32, _D, _D]),
     "cgb_ensemble_partial": (C.c_int, [_P, C.c_char_p, C.c_double, _D, _D]),
     "cgb_device_state": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "cgb_ensemble_partial_device": (C.c_int, [_P, C.c_char_p, C.c_double, _P]),

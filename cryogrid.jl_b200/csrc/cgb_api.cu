@@ -6,6 +6,7 @@
 #include "cgb_lite.cuh"
 #include "cgb_lite_warp.cuh"
 #include "cgb_salt.cuh"
+#include "cgb_init.cuh"
 
 using namespace cgb;
 
@@ -254,7 +255,7 @@ static int finalize(cgb_handle* h)
     double *p_dk, *p_idk, *p_dxc, *p_w1, *p_w2, *p_g, *p_zc;
     rc |= dev_upload(h, &p_dk, dk); rc |= dev_upload(h, &p_idk, idk); rc |= dev_upload(h, &p_dxc, dxc);
     rc |= dev_upload(h, &p_w1, w1); rc |= dev_upload(h, &p_w2, w2); rc |= dev_upload(h, &p_g, g); rc |= dev_upload(h, &p_zc, zc);
-    d.dk = p_dk; d.inv_dk = p_idk; d.dxc = p_dxc; d.eW1 = p_w1; d.eW2 = p_w2; d.eG = p_g;
+    d.zc = p_zc; d.dk = p_dk; d.inv_dk = p_idk; d.dxc = p_dxc; d.eW1 = p_w1; d.eW2 = p_w2; d.eG = p_g;
     d.ctop = 1.0 / (dk[0] / 2.0); d.cbot = 1.0 / (dk[N - 1] / 2.0);
     int* p_cl; rc |= dev_upload(h, &p_cl, h->cell_layer); d.cell_layer = p_cl;
     int first = N - 1;
@@ -401,6 +402,71 @@ extern "C" int cgb_set_state(cgb_handle* h, const double* u, double t0)
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->have_state = true;
     return CGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// on-device initial conditions
+// ------------------------------------------------------------------------------------------------
+static int finish_init(cgb_handle* h, double t0)
+{
+    int thr = 256;
+    k_fill_state<<<(unsigned)((h->M + thr - 1) / thr), thr, 0, h->stream>>>(h->dev.t, h->dev.dt, h->dev.steps, h->dev.iters, h->dev.status, h->M, t0, h->cfg.dt0);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->have_state = true;
+    return CGB_OK;
+}
+
+extern "C" int cgb_init_interp(cgb_handle* h, const double* zk, const double* vk, int64_t nk, int32_t per, double t0)
+{
+    if (!h || !zk || !vk || nk < 1) return CGB_ERR_INVALID;
+    clear_stale_error("cgb_init_interp");
+    if (h->cfg.physics != CGB_PHYSICS_HEAT) CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "cgb_init_interp: heat physics only");
+    if (per != CGB_PER_GLOBAL && per != CGB_PER_COLUMN) CGB_FAIL(h, CGB_ERR_INVALID, "profile values are GLOBAL (nk) or COLUMN (nk*M)");
+    for (int64_t k = 1; k < nk; ++k)
+        if (!(zk[k] > zk[k - 1])) CGB_FAIL(h, CGB_ERR_INVALID, "profile depths must be strictly increasing");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = finalize(h);
+    if (rc) return rc;
+    size_t nv = (size_t)nk * (per == CGB_PER_COLUMN ? (size_t)h->M : 1);
+    double *dz = nullptr, *dv = nullptr;
+    CUDA_TRY(h, cudaMalloc((void**)&dz, nk * sizeof(double)));
+    if (cudaMalloc((void**)&dv, nv * sizeof(double)) != cudaSuccess) { cudaFree(dz); CGB_FAIL(h, CGB_ERR_ALLOC, "profile upload"); }
+    cudaMemcpyAsync(dz, zk, nk * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(dv, vk, nv * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    dim3 grid((unsigned)((h->M + 255) / 256), (unsigned)h->N);
+    k_init_interp<<<grid, 256, 0, h->stream>>>(h->dev, h->dev.zc, dz, dv, (int)nk, per == CGB_PER_COLUMN);
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    cudaStreamSynchronize(h->stream);
+    cudaFree(dz); cudaFree(dv);
+    if (e != cudaSuccess) CGB_FAIL(h, CGB_ERR_CUDA, "k_init_interp: %s", cudaGetErrorString(e));
+    return finish_init(h, t0);
+}
+
+extern "C" int cgb_init_steadystate(cgb_handle* h, const double* T0, int32_t per, double Qgeo, int32_t maxiters, double thresh, double t0)
+{
+    if (!h || !T0) return CGB_ERR_INVALID;
+    clear_stale_error("cgb_init_steadystate");
+    if (h->cfg.physics != CGB_PHYSICS_HEAT) CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "cgb_init_steadystate: heat physics only");
+    if (per != CGB_PER_GLOBAL && per != CGB_PER_COLUMN) CGB_FAIL(h, CGB_ERR_INVALID, "T0 is GLOBAL (1) or COLUMN (M)");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = finalize(h);
+    if (rc) return rc;
+    size_t n0 = per == CGB_PER_COLUMN ? (size_t)h->M : 1;
+    double* d0 = nullptr;
+    CUDA_TRY(h, cudaMalloc((void**)&d0, n0 * sizeof(double)));
+    cudaMemcpyAsync(d0, T0, n0 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    double* Ts = h->d_scratch;                                   // two of the (N+1)*M scratch slots
+    double* kcs = h->d_scratch + (size_t)(h->N + 1) * h->M;
+    k_init_steadystate<<<(unsigned)((h->M + 127) / 128), 128, 0, h->stream>>>(h->dev, h->dev.zc, d0, per == CGB_PER_COLUMN, Qgeo, maxiters, thresh, Ts, kcs);
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    cudaStreamSynchronize(h->stream);
+    cudaFree(d0);
+    if (e != cudaSuccess) CGB_FAIL(h, CGB_ERR_CUDA, "k_init_steadystate: %s", cudaGetErrorString(e));
+    return finish_init(h, t0);
 }
 
 extern "C" int cgb_synchronize(cgb_handle* h)
@@ -751,6 +817,114 @@ extern "C" int cgb_solve_saveat(cgb_handle* h, const double* tsave, int64_t nsav
     }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    return CGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-side output path: save selected cells only + sub-grid thaw depth per column
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gather_rows(const double* __restrict__ src, const int* __restrict__ rows, int nsel, long long M, double* __restrict__ dst)
+{
+    long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    int k = blockIdx.y;
+    if (col < M && k < nsel) dst[(size_t)k * M + col] = src[(size_t)rows[k] * M + col];
+}
+
+// Diagnostics.thawdepth (Diagnostics/permafrost.jl:38-59): first thawed / first frozen cell, linear in between.
+__global__ void __launch_bounds__(128) k_thawdepth(const double* __restrict__ T, const double* __restrict__ zc, int N, long long M, double* __restrict__ out)
+{
+    long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (col >= M) return;
+    int i_frozen = -1, i_thawed = -1;
+    double Tf = 0.0, Tt = 0.0;
+    for (int i = 0; i < N && (i_frozen < 0 || i_thawed < 0); ++i) {
+        double v = T[(size_t)i * M + col];
+        if (i_frozen < 0 && v <= 0.0) { i_frozen = i; Tf = v; }
+        if (i_thawed < 0 && v > 0.0) { i_thawed = i; Tt = v; }
+    }
+    double td;
+    if (i_thawed >= 0 && i_frozen >= 0 && i_thawed < i_frozen) {
+        double z1 = zc[i_thawed], z2 = zc[i_frozen];
+        td = (0.0 - Tt) * (z2 - z1) / (Tf - Tt) + z1;          // solve_depth_linear, Diagnostics.jl:16
+    } else if (i_frozen < 0) td = zc[N - 1];
+    else td = zc[0];
+    out[col] = td;
+}
+
+extern "C" int cgb_solve_saveat_select(cgb_handle* h, const double* tsave, int64_t nsave, const char* vars, const int32_t* cell_index,
+                                       int32_t nsel, double* out, double* thawdepth_out)
+{
+    if (!h || !tsave || !vars || nsave < 1 || (nsel > 0 && (!cell_index || !out)) || (nsel <= 0 && !thawdepth_out)) return CGB_ERR_INVALID;
+    clear_stale_error("cgb_solve_saveat_select");
+    if (!h->have_state) CGB_FAIL(h, CGB_ERR_INVALID, "no state: call cgb_set_state or cgb_init_* first");
+    if (h->cfg.physics != CGB_PHYSICS_HEAT) CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "cgb_solve_saveat_select: heat physics only");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = finalize(h);
+    if (rc) return rc;
+    std::vector<std::string> names;
+    {
+        std::string s(vars), cur;
+        for (char c : s) { if (c == ',') { if (!cur.empty()) names.push_back(cur); cur.clear(); } else if (c != ' ') cur.push_back(c); }
+        if (!cur.empty()) names.push_back(cur);
+    }
+    if (nsel <= 0) names.clear();
+    for (auto& n : names)
+        if (n != "H" && n != "T" && n != "thw") CGB_FAIL(h, CGB_ERR_INVALID, "can save H, T, thw (got '%s')", n.c_str());
+    for (int k = 0; k < nsel; ++k)
+        if (cell_index[k] < 0 || cell_index[k] >= h->N) CGB_FAIL(h, CGB_ERR_INVALID, "cell_index[%d] = %d out of range", k, cell_index[k]);
+    size_t M = (size_t)h->M, NM = (size_t)h->N * M, SM = (size_t)std::max(nsel, 0) * M;
+    size_t per_save = names.size() * SM + (thawdepth_out ? M : 0);
+    if (h->stage_elems < per_save) {
+        for (int i = 0; i < 2; ++i) {
+            if (h->d_stage[i]) cudaFree(h->d_stage[i]);
+            h->d_stage[i] = nullptr;
+            if (cudaMalloc((void**)&h->d_stage[i], per_save * sizeof(double)) != cudaSuccess) CGB_FAIL(h, CGB_ERR_ALLOC, "staging buffer");
+        }
+        h->stage_elems = per_save;
+    }
+    int* d_rows = nullptr;
+    if (nsel > 0) {
+        CUDA_TRY(h, cudaMalloc((void**)&d_rows, nsel * sizeof(int)));
+        CUDA_TRY(h, cudaMemcpyAsync(d_rows, cell_index, nsel * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    }
+    double* fullT = h->d_scratch;                                   // (N+1)*M slots of the diag scratch
+    double* fullW = h->d_scratch + (size_t)(h->N + 1) * M;
+    bool needT = thawdepth_out != nullptr, needW = false;
+    for (auto& n : names) { needT |= n == "T"; needW |= n == "thw"; }
+    for (int64_t s = 0; s < nsave; ++s) {
+        int b = (int)(s & 1);
+        rc = launch_advance(h, tsave[s]);
+        if (rc) { cudaFree(d_rows); return rc; }
+        if (needT || needW) {
+            Diag D{};
+            if (needT) D.T = fullT;
+            if (needW) D.thw = fullW;
+            rc = launch_diag(h, tsave[s], D);
+            if (rc) { cudaFree(d_rows); return rc; }
+        }
+        if (s >= 2) cudaStreamWaitEvent(h->stream, h->stage_free[b], 0);
+        dim3 grid((unsigned)((M + 255) / 256), (unsigned)std::max(nsel, 1));
+        for (size_t v = 0; v < names.size(); ++v) {
+            const double* src = names[v] == "H" ? h->dev.u : (names[v] == "T" ? fullT : fullW);
+            k_gather_rows<<<grid, 256, 0, h->stream>>>(src, d_rows, nsel, (long long)M, h->d_stage[b] + v * SM);
+            h->launches++;
+        }
+        if (thawdepth_out) {
+            k_thawdepth<<<(unsigned)((M + 127) / 128), 128, 0, h->stream>>>(fullT, h->dev.zc, h->N, (long long)M, h->d_stage[b] + names.size() * SM);
+            h->launches++;
+        }
+        cudaEventRecord(h->stage_ready[b], h->stream);
+        cudaStreamWaitEvent(h->copy_stream, h->stage_ready[b], 0);
+        if (!names.empty())
+            cudaMemcpyAsync(out + (size_t)s * names.size() * SM, h->d_stage[b], names.size() * SM * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream);
+        if (thawdepth_out)
+            cudaMemcpyAsync(thawdepth_out + (size_t)s * M, h->d_stage[b] + names.size() * SM, M * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream);
+        cudaEventRecord(h->stage_free[b], h->copy_stream);
+    }
+    cudaError_t e1 = cudaStreamSynchronize(h->stream), e2 = cudaStreamSynchronize(h->copy_stream);
+    cudaFree(d_rows);
+    (void)NM;
+    if (e1 != cudaSuccess || e2 != cudaSuccess) CGB_FAIL(h, CGB_ERR_CUDA, "cgb_solve_saveat_select: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
     return CGB_OK;
 }
 

@@ -72,6 +72,7 @@ struct Dev {
     double ch_w, ch_i, ch_a, ch_m, ch_o, L;
     double g, Lsl, R, rho_w;
     // grid (device arrays)
+    const double* zc;         // [N]   cell midpoints
     const double* dk;         // [N]   cell thickness
     const double* inv_dk;     // [N]
     const double* dxc;        // [N-1] midpoint distances

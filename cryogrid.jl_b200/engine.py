@@ -141,6 +141,26 @@ class Engine(_EngineBase):
             raise ValueError(f"state must have shape {(self.N, self.M)}, got {u.shape}")
         self._check(self.lib.cgb_set_state(self.h, L.dptr(u), float(t0)))
 
+    def initialcondition(self, t0=0.0):
+        """initialcondition!(tile, tspan) on the device, from the tile's initializer (InterpInitializer on :T or
+        ThermalSteadyStateInit).  Equivalent to set_state(model.initialcondition(tile), t0) without the host loop."""
+        from .model import ThermalSteadyStateInit, Profile
+        init = self.tile.inits[0] if self.tile.inits else ("T", Profile((0.0, 0.0)))
+        if isinstance(init, ThermalSteadyStateInit):
+            T0 = L.as_f64(np.broadcast_to(np.asarray(init.T0, dtype=np.float64), (self.tile.M,))[self.columns]
+                          if np.ndim(init.T0) else [float(init.T0)])
+            per = L.PER_COLUMN if np.ndim(init.T0) else L.PER_GLOBAL
+            self._check(self.lib.cgb_init_steadystate(self.h, L.dptr(T0), per, float(init.Qgeo), int(init.maxiters), float(init.thresh), float(t0)))
+            return
+        _, prof = init
+        zk = L.as_f64([p[0] for p in prof])
+        percol = any(np.ndim(p[1]) for p in prof)
+        if percol:
+            vk = L.as_f64(np.stack([np.broadcast_to(np.asarray(p[1], dtype=np.float64), (self.tile.M,))[self.columns] for p in prof]))
+        else:
+            vk = L.as_f64([float(p[1]) for p in prof])
+        self._check(self.lib.cgb_init_interp(self.h, L.dptr(zk), L.dptr(vk), zk.size, L.PER_COLUMN if percol else L.PER_GLOBAL, float(t0)))
+
     def get_state(self, with_time=False):
         u = np.empty((self.N, self.M))
         if not with_time:
@@ -172,6 +192,23 @@ class Engine(_EngineBase):
         assert out.shape == shape and out.flags.c_contiguous and out.dtype == np.float64
         self._check(self.lib.cgb_solve_saveat(self.h, L.dptr(tsave), tsave.size, vars_c.encode(), L.dptr(out)))
         return out
+
+    def solve_saveat_select(self, tsave, savevars=("T",), cells=(), thawdepth=False, out=None, thaw_out=None):
+        """Device-side output path: keep only the cells `cells` of every saved variable (out[nsave, nvars, nsel, M]) and,
+        optionally, the sub-grid thaw depth per column and save (thaw[nsave, M])."""
+        tsave = L.as_f64(tsave)
+        names = {"T": "T", "H": "H", "θw": "thw", "thw": "thw"}
+        cells = np.ascontiguousarray(cells, dtype=np.int32)
+        vars_c = ",".join(names[v] for v in savevars) if cells.size else "T"
+        shape = (tsave.size, len(savevars), cells.size, self.M)
+        if out is None and cells.size:
+            out = np.empty(shape)
+        if thawdepth and thaw_out is None:
+            thaw_out = np.empty((tsave.size, self.M))
+        self._check(self.lib.cgb_solve_saveat_select(
+            self.h, L.dptr(tsave), tsave.size, vars_c.encode(), cells.ctypes.data_as(C.POINTER(C.c_int32)), int(cells.size),
+            L.dptr(out) if cells.size else None, L.dptr(thaw_out) if thawdepth else None))
+        return out, thaw_out
 
     def ensemble_partial(self, var, t):
         s = np.empty(self.N); q = np.empty(self.N)

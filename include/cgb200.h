@@ -150,6 +150,13 @@ int cgb_set_forcing_constant(cgb_handle* h, int32_t which, double value);
 /* ---- state ---------------------------------------------------------------------------------------- */
 /* u0 and t0 (prob.u0, prob.tspan[1]); resets every column's t=t0, dt=dt0, counters and status. */
 int cgb_set_state(cgb_handle* h, const double* u, double t0);
+/* initialcondition!(tile, tspan) evaluated ON THE DEVICE (Tiles/tile.jl:187-200), so that remade ensemble members do not
+ * go through a serial host loop (problem.jl:117-119).  Both reset t = t0, dt = dt0, counters and status like cgb_set_state.
+ *  - InterpInitializer(:T, profile) + initialize_soil_heat! (initializers.jl:42-67, Soils/soil_heat.jl:38-63):
+ *    zk[nk] depths, vk[nk] (per = CGB_PER_GLOBAL) or vk[k*M + col] (per = CGB_PER_COLUMN); linear in depth, flat outside.
+ *  - ThermalSteadyStateInit(T0, Qgeo, maxiters, thresh) (Heat/heat_init.jl:58-85); T0 has 1 (GLOBAL) or M (COLUMN) values. */
+int cgb_init_interp(cgb_handle* h, const double* zk, const double* vk, int64_t nk, int32_t per, double t0);
+int cgb_init_steadystate(cgb_handle* h, const double* T0, int32_t per, double Qgeo, int32_t maxiters, double thresh, double t0);
 /* u, and optionally per-column t and dt (either may be NULL). This is also the checkpoint. */
 int cgb_get_state(cgb_handle* h, double* u, double* t, double* dt);
 /* per-column status words / step counts (M entries each, either may be NULL) */
@@ -175,6 +182,14 @@ int cgb_get_diag(cgb_handle* h, const char* var, double t, double* out);
  * vars: comma-separated subset of "H,T,thw".  out is a HOST pointer (pinned or pageable); copies are
  * overlapped with stepping on a second stream. */
 int cgb_solve_saveat(cgb_handle* h, const double* tsave, int64_t nsave, const char* vars, double* out);
+
+/* Device-side output path: like cgb_solve_saveat, but only the cells cell_index[0..nsel) are kept --
+ * out[((s*nvars + v)*nsel + k)*M + col] -- which is what users read from CryoGridOutput (out.T[Z(Near(zs))],
+ * examples/cglite_parameter_ensembles.jl:96) -- and, if thawdepth_out != NULL, the sub-grid thaw depth of every column at
+ * every save, thawdepth_out[s*M + col] (Diagnostics.thawdepth, Diagnostics/permafrost.jl:38-59; its yearly maximum is the
+ * active layer thickness, :66-72).  nsel may be 0 to return thaw depths only.  Host pointers. */
+int cgb_solve_saveat_select(cgb_handle* h, const double* tsave, int64_t nsave, const char* vars, const int32_t* cell_index,
+                            int32_t nsel, double* out, double* thawdepth_out);
 
 /* ---- ensemble statistics / multi-GPU seams -------------------------------------------------------- */
 /* Local (this handle's columns) sums for ensemble moments of a diagnostic at the current state:

@@ -299,3 +299,54 @@ def test_reciprocal_sequences_accuracy():
     print(f"rcp rel. error: raw {e_raw:.3e} (2^{np.log2(e_raw):.1f}), newton2 {e_n2:.3e}, cubic {e_c3:.3e}")
     assert e_n2 < 3e-16          # <= ~1.3 ulp
     assert e_raw < 2.0 ** -16
+
+
+def test_device_initialcondition_interp(orc):
+    # InterpInitializer + initialize_soil_heat! on the device vs the host mirror and the oracle
+    for tile in (common.samoylov_freew_tile(ncolumns=9, seed=3), common.sfcc_tile(ncolumns=5, kind="painterkarra", solver="lut")):
+        H_host = cg.initialcondition(tile)
+        eng = cg.Engine(tile)
+        eng.initialcondition(0.0)
+        H_dev, t, dt = eng.get_state(with_time=True)
+        np.testing.assert_allclose(H_dev, H_host, rtol=1e-13, atol=1e-6)
+        assert np.all(t == 0.0) and np.all(dt == 60.0)
+        eng.advance_to(3600.0)            # the state is usable right away
+        eng.close()
+    # per-column temperature profiles
+    tile = common.samoylov_freew_tile(ncolumns=4, seed=5)
+    Tsurf = np.array([-5.0, -1.0, 0.5, 3.0])
+    tile.inits = (cg.initializer("T", cg.TemperatureProfile((0.0, Tsurf), (10.0, -2.0), (1000.0, 10.0))),)
+    eng = cg.Engine(tile)
+    eng.initialcondition(0.0)
+    np.testing.assert_allclose(eng.get_state(), cg.initialcondition(tile), rtol=1e-13, atol=1e-6)
+    eng.close()
+
+
+def _thawdepth_ref(T, z):
+    # Diagnostics.thawdepth (Diagnostics/permafrost.jl:38-59) restated
+    fr = np.nonzero(T <= 0.0)[0]; th = np.nonzero(T > 0.0)[0]
+    if th.size and fr.size and th[0] < fr[0]:
+        return (0.0 - T[th[0]]) * (z[fr[0]] - z[th[0]]) / (T[fr[0]] - T[th[0]]) + z[th[0]]
+    return z[-1] if fr.size == 0 else z[0]
+
+
+def test_device_output_path_select_and_thawdepth():
+    # selected depths + thaw depth computed on the device == post-processing of the full output
+    tile = common.samoylov_freew_tile(ncolumns=33, seed=7)
+    H0 = cg.initialcondition(tile)
+    days = np.array([120.0, 150.0, 180.0, 200.0]) * 86400.0
+    eng = cg.Engine(tile, dtmax=600.0)
+    eng.set_state(H0, 0.0)
+    full = eng.solve_saveat(days, ("T", "θw"))
+    z = tile.grid.cells
+    cells = np.array([np.argmin(np.abs(z - d)) for d in (0.01, 0.1, 0.5, 1.0, 2.0, 10.0, 20.0)], dtype=np.int32)
+    eng.set_state(H0, 0.0)
+    sel, thaw = eng.solve_saveat_select(days, ("T", "θw"), cells, thawdepth=True)
+    np.testing.assert_array_equal(sel, full[:, :, cells, :])
+    ref = np.array([[_thawdepth_ref(full[s, 0, :, c], z) for c in range(tile.M)] for s in range(days.size)])
+    np.testing.assert_allclose(thaw, ref, rtol=1e-13, atol=1e-13)
+    assert thaw[0].max() > 0.1            # Tair peaks at day 91: the active layer is open at day 120
+    eng.set_state(H0, 0.0)
+    _, thaw2 = eng.solve_saveat_select(days, (), (), thawdepth=True)
+    np.testing.assert_array_equal(thaw2, thaw)
+    eng.close()

@@ -152,3 +152,18 @@ def test_lite_warp_vs_thread_other_grids(orc, grid_name):
         eng.close()
     finally:
         del os.environ["CGB_LITE_VARIANT"]
+
+
+def test_device_steadystate_init(orc):
+    # ThermalSteadyStateInit on the device vs the oracle (Heat/heat_init.jl:58-85)
+    tile = common.lite_ensemble_tile(ncolumns=37, seed=1234)
+    eng = cg.Engine(tile, stepper="lite")
+    eng.initialcondition(0.0)
+    H = eng.get_state()
+    assert np.all(np.isfinite(H))
+    for c in range(0, tile.M, 6):
+        Href = orc.OracleColumn(tile, c).steadystate_init(-15.0, 0.053)
+        np.testing.assert_allclose(H[:, c], Href, rtol=1e-9, atol=1e-2)
+    eng.advance_to(86400.0)
+    assert not eng.status()[0].any()
+    eng.close()
