@@ -1,11 +1,7 @@
 // cgb_api.cu -- C ABI of libcgb200.so (see include/cgb200.h). Host-side bookkeeping + kernel launches.
 // There is no CPU path here: without a CUDA device cgb_create fails with CGB_ERR_NO_DEVICE.
 #include "cgb_handle.h"
-#include "cgb_euler.cuh"
-#include "cgb_euler_fast.cuh"
-#include "cgb_lite.cuh"
-#include "cgb_lite_warp.cuh"
-#include "cgb_salt.cuh"
+#include "cgb_launch.h"
 #include "cgb_init.cuh"
 
 using namespace cgb;
@@ -372,7 +368,7 @@ static int finalize(cgb_handle* h)
     d.lite_miniters = h->cfg.lite_miniters; d.lite_maxiters = h->cfg.lite_maxiters; d.lite_tol = h->cfg.lite_tol;
     if (rc) return rc;
     // heat+salt extras
-    rc = salt_finalize(h, zc);
+    rc = cgb_salt_finalize(h, zc);
     if (rc) return rc;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->dirty = false;
@@ -401,6 +397,7 @@ extern "C" int cgb_set_state(cgb_handle* h, const double* u, double t0)
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->have_state = true;
+    h->t_front = t0;
     return CGB_OK;
 }
 
@@ -415,6 +412,7 @@ static int finish_init(cgb_handle* h, double t0)
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->have_state = true;
+    h->t_front = t0;
     return CGB_OK;
 }
 
@@ -549,140 +547,38 @@ static bool all_freewater(const cgb_handle* h)
     return true;
 }
 
-template <int CPL, int MODE, bool DIAG>
-static int launch_euler_t(cgb_handle* h, double t_target, const Diag& D)
-{
-    auto kern = k_heat_euler<CPL, MODE, DIAG>;
-    size_t smem = (size_t)(5 * CPL * 32 + 4 * h->nl * LC_STRIDE) * sizeof(double);
-    static int blocks_per_sm = 0;   // per instantiation
-    if (blocks_per_sm == 0) {
-        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, 128, smem));
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
-    }
-    long long tiles = (h->M + 3) / 4;
-    long long grid = std::min<long long>(tiles, (long long)h->num_sms * blocks_per_sm);
-    CUDA_TRY(h, cudaMemsetAsync(h->dev.counter, 0, sizeof(unsigned long long), h->stream));
-    kern<<<(unsigned)grid, 128, smem, h->stream>>>(h->dev, t_target, D);
-    h->launches++;
-    CUDA_TRY(h, cudaGetLastError());
-    return CGB_OK;
-}
+static int launch_advance_inner(cgb_handle* h, double t_target, double* saveT, double* saveW);
 
-template <int MODE, bool DIAG>
-static int launch_euler_c(cgb_handle* h, double t_target, const Diag& D)
+// saveT / saveW (device pointers, N*M, may be null): where the stepping kernel leaves the diagnostics the reference would
+// SAVE at t_target -- the cache of the last RHS evaluation of the interval (see cgb_solve_saveat).
+static int launch_advance(cgb_handle* h, double t_target, double* saveT = nullptr, double* saveW = nullptr)
 {
-    int cpl = (h->N + 31) / 32;
-    switch (cpl) {
-    case 1: return launch_euler_t<1, MODE, DIAG>(h, t_target, D);
-    case 2: return launch_euler_t<2, MODE, DIAG>(h, t_target, D);
-    case 3: case 4: return launch_euler_t<4, MODE, DIAG>(h, t_target, D);
-    case 5: case 6: return launch_euler_t<6, MODE, DIAG>(h, t_target, D);
-    case 7: return launch_euler_t<7, MODE, DIAG>(h, t_target, D);
-    case 8: return launch_euler_t<8, MODE, DIAG>(h, t_target, D);
-    case 9: return launch_euler_t<9, MODE, DIAG>(h, t_target, D);
-    case 10: return launch_euler_t<10, MODE, DIAG>(h, t_target, D);
-    case 11: case 12: return launch_euler_t<12, MODE, DIAG>(h, t_target, D);
-    default: return launch_euler_t<16, MODE, DIAG>(h, t_target, D);
-    }
-}
-
-static int launch_advance_inner(cgb_handle* h, double t_target);
-
-static int launch_advance(cgb_handle* h, double t_target)
-{
-    if (!h->profiling) return launch_advance_inner(h, t_target);
+    h->t_front = std::max(h->t_front, t_target);
+    if (!h->profiling) return launch_advance_inner(h, t_target, saveT, saveW);
     cudaEvent_t a, b;
     CUDA_TRY(h, cudaEventCreate(&a));
     CUDA_TRY(h, cudaEventCreate(&b));
     CUDA_TRY(h, cudaEventRecord(a, h->stream));
-    int rc = launch_advance_inner(h, t_target);
+    int rc = launch_advance_inner(h, t_target, saveT, saveW);
     CUDA_TRY(h, cudaEventRecord(b, h->stream));
     h->prof_events.emplace_back(a, b);
     return rc;
 }
 
-static int fast_cubic()
-{
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("CGB_FAST_CUBIC"); v = e ? atoi(e) : 1; }
-    return v;
-}
-
-template <int CPL, int MINB, bool CUBIC>
-static int launch_fast_tb(cgb_handle* h, double t_target)
-{
-    auto kern = k_heat_euler_fast<CPL, MINB, CUBIC>;
-    size_t smem = (size_t)(4 * h->nl * FC_STRIDE) * sizeof(double);
-    static int blocks_per_sm = 0;   // per instantiation
-    if (blocks_per_sm == 0) {
-        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, 128, smem));
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
-    }
-    long long tiles = (h->M + 3) / 4;
-    long long grid = std::min<long long>(tiles, (long long)h->num_sms * blocks_per_sm);
-    CUDA_TRY(h, cudaMemsetAsync(h->dev.counter, 0, sizeof(unsigned long long), h->stream));
-    kern<<<(unsigned)grid, 128, smem, h->stream>>>(h->dev, t_target);
-    h->launches++;
-    CUDA_TRY(h, cudaGetLastError());
-    return CGB_OK;
-}
-
-// Register budget of the fast kernel: MINB resident CTAs (x4 warps) per SM.  Tuned on B200 (profiles/): see DESIGN.md.
-static int fast_minb()
-{
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("CGB_FAST_MINB"); v = e ? atoi(e) : 3; if (v < 2 || v > 4) v = 3; }
-    return v;
-}
-
-template <int CPL>
-static int launch_fast_t(cgb_handle* h, double t_target)
-{
-    if (fast_cubic()) {
-        switch (fast_minb()) {
-        case 2: return launch_fast_tb<CPL, 2, true>(h, t_target);
-        case 4: return launch_fast_tb<CPL, 4, true>(h, t_target);
-        default: return launch_fast_tb<CPL, 3, true>(h, t_target);
-        }
-    }
-    switch (fast_minb()) {
-    case 2: return launch_fast_tb<CPL, 2, false>(h, t_target);
-    case 4: return launch_fast_tb<CPL, 4, false>(h, t_target);
-    default: return launch_fast_tb<CPL, 3, false>(h, t_target);
-    }
-}
-
-static int launch_fast(cgb_handle* h, double t_target)
-{
-    int cpl = (h->N + 31) / 32;
-    switch (cpl) {
-    case 1: return launch_fast_t<1>(h, t_target);
-    case 2: return launch_fast_t<2>(h, t_target);
-    case 3: case 4: return launch_fast_t<4>(h, t_target);
-    case 5: case 6: return launch_fast_t<6>(h, t_target);
-    case 7: return launch_fast_t<7>(h, t_target);
-    case 8: return launch_fast_t<8>(h, t_target);
-    case 9: return launch_fast_t<9>(h, t_target);
-    case 10: return launch_fast_t<10>(h, t_target);
-    case 11: case 12: return launch_fast_t<12>(h, t_target);
-    default: return launch_fast_t<16>(h, t_target);
-    }
-}
-
-static int launch_advance_inner(cgb_handle* h, double t_target)
+static int launch_advance_inner(cgb_handle* h, double t_target, double* saveT, double* saveW)
 {
     Diag D{};
-    if (h->cfg.physics == CGB_PHYSICS_HEAT_SALT) return salt_launch(h, t_target, false, D, nullptr);
+    D.T = saveT; D.thw = saveW;
+    if (h->cfg.physics == CGB_PHYSICS_HEAT_SALT) return cgb_salt_launch(h, t_target, false, D, nullptr);
     if (h->cfg.stepper == CGB_STEPPER_LITE_IMPLICIT) {
         // "Thomas per thread or partition/PCR per warp": the warp variant is the default; CGB_LITE_VARIANT=thread selects
         // the reference-order Thomas sweep (re-read on every launch so that tests can switch in-process)
         const char* v = getenv("CGB_LITE_VARIANT");
-        if (v && std::strcmp(v, "thread") == 0) return lite_launch(h, t_target, false, D);
-        return lite_warp_launch(h, t_target);
+        if (v && std::strcmp(v, "thread") == 0) return cgb_launch_lite_thread(h, t_target, false, D);
+        return cgb_launch_lite_warp(h, t_target, saveT, saveW);
     }
     bool fast = all_freewater(h) && h->cfg.limiter == CGB_LIMITER_MAXDELTA && h->fast_ok;
-    if (fast) return launch_fast(h, t_target);
+    if (fast) return cgb_launch_fast(h, t_target, saveT, saveW);
     // solver mode of the general kernel: 1 = every layer SFCC + LUT, 2 = every layer SFCC + Newton, 3 = every layer FreeWater, 0 = mixed
     bool all_lut = true, all_newton = true;
     for (int l = 0; l < h->nl; ++l) {
@@ -690,16 +586,16 @@ static int launch_advance_inner(cgb_handle* h, double t_target)
         all_lut &= sf && h->fc_solver[l] == CGB_SOLVER_LUT;
         all_newton &= sf && h->fc_solver[l] == CGB_SOLVER_NEWTON;
     }
-    if (all_lut) return launch_euler_c<1, false>(h, t_target, D);
-    if (all_newton) return launch_euler_c<2, false>(h, t_target, D);
-    if (all_freewater(h)) return launch_euler_c<3, false>(h, t_target, D);
-    return launch_euler_c<0, false>(h, t_target, D);
+    if (all_lut) return cgb_launch_euler(h, 1, false, t_target, D);
+    if (all_newton) return cgb_launch_euler(h, 2, false, t_target, D);
+    if (all_freewater(h)) return cgb_launch_euler(h, 3, false, t_target, D);
+    return cgb_launch_euler(h, 0, false, t_target, D);
 }
 
 static int launch_diag(cgb_handle* h, double t, const Diag& D)
 {
-    if (h->cfg.stepper == CGB_STEPPER_LITE_IMPLICIT) return lite_launch(h, t, true, D);
-    return launch_euler_c<0, true>(h, t, D);
+    if (h->cfg.stepper == CGB_STEPPER_LITE_IMPLICIT) return cgb_launch_lite_thread(h, t, true, D);
+    return cgb_launch_euler(h, 0, true, t, D);
 }
 
 extern "C" int cgb_advance_to(cgb_handle* h, double t_target)
@@ -737,7 +633,7 @@ extern "C" int cgb_get_diag(cgb_handle* h, const char* var, double t, double* ou
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     int rc = finalize(h);
     if (rc) return rc;
-    if (h->cfg.physics == CGB_PHYSICS_HEAT_SALT) return salt_get_diag(h, var, t, out);
+    if (h->cfg.physics == CGB_PHYSICS_HEAT_SALT) return cgb_salt_get_diag(h, var, t, out);
     Diag D{};
     double* p; size_t cnt;
     rc = diag_slot(h, var, D, &p, &cnt);
@@ -767,29 +663,63 @@ extern "C" int cgb_rhs(cgb_handle* h, double t, double* du_out)
 // ------------------------------------------------------------------------------------------------
 // solve(prob; saveat): advance + save, D2H overlapped on a second stream
 // ------------------------------------------------------------------------------------------------
+// Parses "H,T,thw,T_now,thw_now" and runs one save interval: advance to t with the reference-verbatim diagnostics (cache of
+// the last RHS evaluation) fused into the stepping kernel, plus a DIAG launch only for *_now variables or zero-step saves.
+struct SaveVars {
+    std::vector<std::string> names;
+    bool T = false, W = false, Tnow = false, Wnow = false;
+};
+
+static int parse_savevars(cgb_handle* h, const char* vars, SaveVars& sv)
+{
+    std::string s(vars), cur;
+    for (char c : s) { if (c == ',') { if (!cur.empty()) sv.names.push_back(cur); cur.clear(); } else if (c != ' ') cur.push_back(c); }
+    if (!cur.empty()) sv.names.push_back(cur);
+    for (auto& n : sv.names) {
+        if (n == "T") sv.T = true; else if (n == "thw") sv.W = true; else if (n == "T_now") sv.Tnow = true; else if (n == "thw_now") sv.Wnow = true;
+        else if (n != "H") CGB_FAIL(h, CGB_ERR_INVALID, "saved variables are H, T, thw, T_now, thw_now (got '%s')", n.c_str());
+    }
+    return CGB_OK;
+}
+
+// fills bufT/bufW (verbatim) and nowT/nowW (recomputed at the saved state); any pointer may be null when not needed
+static int advance_and_save(cgb_handle* h, double t, const SaveVars& sv, double* bufT, double* bufW, double* nowT, double* nowW)
+{
+    bool moved = t > h->t_front;          // otherwise no step is taken: the cache IS the state at t (initial save, basic_solvers.jl:33-37)
+    int rc = launch_advance(h, t, (sv.T && moved) ? bufT : nullptr, (sv.W && moved) ? bufW : nullptr);
+    if (rc) return rc;
+    Diag D{};
+    if (sv.Tnow) D.T = nowT;
+    if (sv.Wnow) D.thw = nowW;
+    bool need = sv.Tnow || sv.Wnow;
+    if (!moved) {
+        if (sv.T) { if (sv.Tnow) { /* copied below */ } else D.T = bufT; need = true; }
+        if (sv.W) { if (sv.Wnow) { } else D.thw = bufW; need = true; }
+    }
+    if (need) { rc = launch_diag(h, t, D); if (rc) return rc; }
+    size_t NM = (size_t)h->N * h->M;
+    if (!moved && sv.T && sv.Tnow) CUDA_TRY(h, cudaMemcpyAsync(bufT, nowT, NM * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (!moved && sv.W && sv.Wnow) CUDA_TRY(h, cudaMemcpyAsync(bufW, nowW, NM * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return CGB_OK;
+}
+
 extern "C" int cgb_solve_saveat(cgb_handle* h, const double* tsave, int64_t nsave, const char* vars, double* out)
 {
-    clear_stale_error("cgb_solve_saveat");
     if (!h || !tsave || !vars || !out || nsave < 1) return CGB_ERR_INVALID;
+    clear_stale_error("cgb_solve_saveat");
     if (!h->have_state) CGB_FAIL(h, CGB_ERR_INVALID, "cgb_set_state has not been called");
     if (h->cfg.physics == CGB_PHYSICS_HEAT_SALT) CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "cgb_solve_saveat: heat+salt uses cgb_advance_to + cgb_get_state");
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     int rc = finalize(h);
     if (rc) return rc;
-    std::vector<std::string> names;
-    {
-        std::string s(vars), cur;
-        for (char c : s) { if (c == ',') { if (!cur.empty()) names.push_back(cur); cur.clear(); } else if (c != ' ') cur.push_back(c); }
-        if (!cur.empty()) names.push_back(cur);
-    }
-    if (names.empty()) CGB_FAIL(h, CGB_ERR_INVALID, "no variables to save");
-    for (auto& n : names)
-        if (n != "H" && n != "T" && n != "thw") CGB_FAIL(h, CGB_ERR_INVALID, "cgb_solve_saveat can save H, T, thw (got '%s')", n.c_str());
-    size_t NM = (size_t)h->N * h->M, per_save = NM * names.size();
+    SaveVars sv;
+    rc = parse_savevars(h, vars, sv);
+    if (rc) return rc;
+    if (sv.names.empty()) CGB_FAIL(h, CGB_ERR_INVALID, "no variables to save");
+    size_t NM = (size_t)h->N * h->M, per_save = NM * sv.names.size();
     if (h->stage_elems < per_save) {
         for (int i = 0; i < 2; ++i) {
             if (h->d_stage[i]) cudaFree(h->d_stage[i]);
-        if (i == 0 && h->d_lite) cudaFree(h->d_lite);
             h->d_stage[i] = nullptr;
             cudaError_t e = cudaMalloc((void**)&h->d_stage[i], per_save * sizeof(double));
             if (e != cudaSuccess) CGB_FAIL(h, CGB_ERR_ALLOC, "staging buffer: %s", cudaGetErrorString(e));
@@ -798,18 +728,18 @@ extern "C" int cgb_solve_saveat(cgb_handle* h, const double* tsave, int64_t nsav
     }
     for (int64_t s = 0; s < nsave; ++s) {
         int b = (int)(s & 1);
-        rc = launch_advance(h, tsave[s]);
-        if (rc) return rc;
+        // the stepping kernel writes straight into staging buffer b: it must have been drained by the copy of save s-2
         if (s >= 2) CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->stage_free[b], 0));
-        Diag D{};
-        bool need_diag = false;
-        for (size_t v = 0; v < names.size(); ++v) {
+        double *bT = nullptr, *bW = nullptr, *nT = nullptr, *nW = nullptr;
+        for (size_t v = 0; v < sv.names.size(); ++v) {
             double* dst = h->d_stage[b] + v * NM;
-            if (names[v] == "H") CUDA_TRY(h, cudaMemcpyAsync(dst, h->dev.u, NM * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-            else if (names[v] == "T") { D.T = dst; need_diag = true; }
-            else { D.thw = dst; need_diag = true; }
+            if (sv.names[v] == "T") bT = dst; else if (sv.names[v] == "thw") bW = dst;
+            else if (sv.names[v] == "T_now") nT = dst; else if (sv.names[v] == "thw_now") nW = dst;
         }
-        if (need_diag) { rc = launch_diag(h, tsave[s], D); if (rc) return rc; }
+        rc = advance_and_save(h, tsave[s], sv, bT, bW, nT, nW);
+        if (rc) return rc;
+        for (size_t v = 0; v < sv.names.size(); ++v)
+            if (sv.names[v] == "H") CUDA_TRY(h, cudaMemcpyAsync(h->d_stage[b] + v * NM, h->dev.u, NM * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         CUDA_TRY(h, cudaEventRecord(h->stage_ready[b], h->stream));
         CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->stage_ready[b], 0));
         CUDA_TRY(h, cudaMemcpyAsync(out + (size_t)s * per_save, h->d_stage[b], per_save * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
@@ -861,15 +791,9 @@ extern "C" int cgb_solve_saveat_select(cgb_handle* h, const double* tsave, int64
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     int rc = finalize(h);
     if (rc) return rc;
-    std::vector<std::string> names;
-    {
-        std::string s(vars), cur;
-        for (char c : s) { if (c == ',') { if (!cur.empty()) names.push_back(cur); cur.clear(); } else if (c != ' ') cur.push_back(c); }
-        if (!cur.empty()) names.push_back(cur);
-    }
-    if (nsel <= 0) names.clear();
-    for (auto& n : names)
-        if (n != "H" && n != "T" && n != "thw") CGB_FAIL(h, CGB_ERR_INVALID, "can save H, T, thw (got '%s')", n.c_str());
+    SaveVars sv;
+    if (nsel > 0) { rc = parse_savevars(h, vars, sv); if (rc) return rc; }
+    std::vector<std::string>& names = sv.names;
     for (int k = 0; k < nsel; ++k)
         if (cell_index[k] < 0 || cell_index[k] >= h->N) CGB_FAIL(h, CGB_ERR_INVALID, "cell_index[%d] = %d out of range", k, cell_index[k]);
     size_t M = (size_t)h->M, NM = (size_t)h->N * M, SM = (size_t)std::max(nsel, 0) * M;
@@ -887,25 +811,21 @@ extern "C" int cgb_solve_saveat_select(cgb_handle* h, const double* tsave, int64
         CUDA_TRY(h, cudaMalloc((void**)&d_rows, nsel * sizeof(int)));
         CUDA_TRY(h, cudaMemcpyAsync(d_rows, cell_index, nsel * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     }
-    double* fullT = h->d_scratch;                                   // (N+1)*M slots of the diag scratch
+    // full-depth fields land in the four (N+1)*M slots of the diag scratch, the selected rows are gathered from there
+    double* fullT = h->d_scratch;
     double* fullW = h->d_scratch + (size_t)(h->N + 1) * M;
-    bool needT = thawdepth_out != nullptr, needW = false;
-    for (auto& n : names) { needT |= n == "T"; needW |= n == "thw"; }
+    double* nowT = h->d_scratch + 2 * (size_t)(h->N + 1) * M;
+    double* nowW = h->d_scratch + 3 * (size_t)(h->N + 1) * M;
+    SaveVars need = sv;
+    need.T |= thawdepth_out != nullptr;           // thaw depth is computed from the saved T, as Diagnostics.thawdepth(out.T) does
     for (int64_t s = 0; s < nsave; ++s) {
         int b = (int)(s & 1);
-        rc = launch_advance(h, tsave[s]);
+        rc = advance_and_save(h, tsave[s], need, fullT, fullW, nowT, nowW);
         if (rc) { cudaFree(d_rows); return rc; }
-        if (needT || needW) {
-            Diag D{};
-            if (needT) D.T = fullT;
-            if (needW) D.thw = fullW;
-            rc = launch_diag(h, tsave[s], D);
-            if (rc) { cudaFree(d_rows); return rc; }
-        }
         if (s >= 2) cudaStreamWaitEvent(h->stream, h->stage_free[b], 0);
         dim3 grid((unsigned)((M + 255) / 256), (unsigned)std::max(nsel, 1));
         for (size_t v = 0; v < names.size(); ++v) {
-            const double* src = names[v] == "H" ? h->dev.u : (names[v] == "T" ? fullT : fullW);
+            const double* src = names[v] == "H" ? h->dev.u : names[v] == "T" ? fullT : names[v] == "thw" ? fullW : names[v] == "T_now" ? nowT : nowW;
             k_gather_rows<<<grid, 256, 0, h->stream>>>(src, d_rows, nsel, (long long)M, h->d_stage[b] + v * SM);
             h->launches++;
         }

@@ -248,7 +248,7 @@ __device__ __forceinline__ double lut_eval_cached(const double* __restrict__ Hk,
 // x^n and (1+x^n)^-m for x > 0 through exp/log.  Out of line on purpose: two exp + two log are ~200 instructions, and the
 // callers are unrolled over the cells of a lane (and sit inside the Newton loop) -- inlined, the step loop overflows the
 // instruction cache (ncu: `no_instruction` was the second largest stall).
-__device__ __noinline__ void vg_powers(double x, double n, double m, double& xn, double& pb)
+static __device__ __noinline__ void vg_powers(double x, double n, double m, double& xn, double& pb)
 {
     xn = exp(n * log(x));
     pb = exp(-m * log1p(xn));

@@ -281,6 +281,18 @@ __global__ void __launch_bounds__(128) k_heat_euler(const __grid_constant__ Dev 
             for (int j = 0; j < CPL; ++j)
                 freezethaw_cell<MODE, DIAG>(P, lcw + loff[j], H[j], dC, dK, T[j], thw[j], C[j], dHdT[j], dth[j], kc[j]);
 
+            if (!DIAG && (D.T || D.thw) && !(t + dt < t_target)) {
+                // last step of the interval: the reference saves the diagnostics cached by this RHS evaluation (state BEFORE
+                // the step): problem.jl:67-68, Numerics/statevars.jl:81-106, basic_solvers.jl:61-66
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) {
+                    int i = lane * CPL + j;
+                    if (i < N) {
+                        if (D.T) D.T[(size_t)i * M + col] = T[j];
+                        if (D.thw) D.thw[(size_t)i * M + col] = thw[j];
+                    }
+                }
+            }
             // ---- stage B/C: edge fluxes (upper edge of every local cell)
             double Tup = __shfl_up_sync(FULL, T[CPL - 1], 1);
             double kup = __shfl_up_sync(FULL, kc[CPL - 1], 1);

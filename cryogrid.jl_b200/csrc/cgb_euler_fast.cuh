@@ -17,7 +17,7 @@
 namespace cgb {
 
 constexpr int FC_STRIDE = 8;   // fast-path per-(column,layer) constants
-enum FastConst { FC_LTH = 0, FC_INVLTH, FC_CB, FC_KB, FC_DCTH, FC_DKTH };
+enum FastConst { FC_LTH = 0, FC_INVLTH, FC_CB, FC_KB, FC_DCTH, FC_DKTH, FC_THWI };
 
 __device__ __forceinline__ double warp_max_nonneg(double v)
 {
@@ -31,8 +31,8 @@ __device__ __forceinline__ double warp_max_nonneg(double v)
 template <bool CUBIC>
 __device__ __forceinline__ double rcp_sel(double a) { return CUBIC ? rcp_fast3(a) : rcp_fast(a); }
 
-template <int CPL, int MINB, bool CUBIC>
-__global__ void __launch_bounds__(128, MINB) k_heat_euler_fast(const __grid_constant__ Dev P, double t_target)
+template <int CPL, int MINB, bool CUBIC, bool SAVE>
+__global__ void __launch_bounds__(128, MINB) k_heat_euler_fast(const __grid_constant__ Dev P, double t_target, double* __restrict__ saveT, double* __restrict__ saveW)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31;
@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(128, MINB) k_heat_euler_fast(const __grid_cons
             c[FC_KB] = P.sk_i * thwi + P.sk_a * tha + P.sk_m * thm + P.sk_o * tho;
             c[FC_DCTH] = dC * thwi;
             c[FC_DKTH] = dK * thwi;
+            c[FC_THWI] = thwi;
         }
         __syncwarp();
 
@@ -164,6 +165,23 @@ __global__ void __launch_bounds__(128, MINB) k_heat_euler_fast(const __grid_cons
         stage_a();
         while (t < t_target) {
             if (fkind == 2 && (t < ft_first || t > ft_last)) { status |= 4; break; }     // providers.jl:30-33
+            if (SAVE && !(t + dt < t_target)) {
+                // Last step of the interval: what the reference SAVES for diagnostic variables is the cache of this (the last)
+                // RHS evaluation, i.e. T, θw of the state BEFORE the step (problem.jl:67-68 -> Numerics/statevars.jl:81-106
+                // retrieve(); CGEuler evaluates the tile before u += dt*du, basic_solvers.jl:61-66).  Reproduced verbatim.
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) {
+                    int i = lane * CPL + j;
+                    if (i < N) {
+                        if (saveT) saveT[(size_t)i * M + col] = T[j];
+                        if (saveW) {
+                            const double* c = lcw + loff[j];
+                            double hc = sel_min(relu_bits(H[j]), c[FC_LTH]);
+                            saveW[(size_t)i * M + col] = (hc * c[FC_INVLTH]) * c[FC_THWI];
+                        }
+                    }
+                }
+            }
             // ---- edge fluxes (upper edge of every local cell): harmonic mean + flux with one reciprocal
             double Tup = __shfl_up_sync(FULL, T[CPL - 1], 1);
             double kup = __shfl_up_sync(FULL, kc[CPL - 1], 1);

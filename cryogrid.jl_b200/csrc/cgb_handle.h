@@ -40,6 +40,7 @@ struct cgb_handle {
     struct HostForcing { int kind = 0; double value = 0, period = 1, amp = 0, phase = 0, level = 0; std::vector<double> t, y; } forc[2];
     bool dirty = true;        // device copy of the description is stale
     bool have_state = false;
+    double t_front = 0.0;     // latest time any advance was asked to reach (host-side bookkeeping for the save path)
     bool fast_ok = false;     // FreeWater fast kernel applicable (set by finalize)
     // device memory
     std::vector<void*> allocs;

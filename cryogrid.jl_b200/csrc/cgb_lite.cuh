@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(128) k_lite_thomas(const __grid_constant__ Dev
                     if (i == 0) { cpi = Cc / B; dpi = Dd / B; }                 // math.jl:176-190
                     else { double temp = B - A * cp_prev; cpi = Cc / temp; dpi = (Dd - A * dp_prev) / temp; }
                     S.cp[o] = cpi; S.dp[o] = dpi; S.T[o] = cur.T; S.dHdT[o] = cur.dHdT;
+                    if (D.thw) D.thw[o] = cur.thw;          // saved θw = cache of the last tile evaluation
                     cp_prev = cpi; dp_prev = dpi;
                 }
                 prev = cur; cur = nxt; Hcur = Hnxt; k_up = k_dn;
@@ -177,6 +178,8 @@ __global__ void __launch_bounds__(128) k_lite_thomas(const __grid_constant__ Dev
         if (status & (2 | 4)) break;
     }
     if (!DIAG) {
+        if (D.T && nsteps > 0)
+            for (int i = 0; i < N; ++i) D.T[(size_t)i * M + col] = S.T[(size_t)i * M + col];   // saved T: last tile evaluation
         P.t[col] = t; P.dt[col] = dt; P.steps[col] += nsteps; P.iters[col] += niter;
         if (status) P.status[col] |= status;
     }

@@ -20,8 +20,8 @@
 
 namespace cgb {
 
-template <int CPL, int MODE>
-__global__ void __launch_bounds__(128, 2) k_lite_warp(const __grid_constant__ Dev P, double t_target)
+template <int CPL, int MODE, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__ Dev P, double t_target, double* __restrict__ saveT, double* __restrict__ saveW)
 {
     extern __shared__ double smem[];
     double* sDk = smem;                    // [CPL*32] cell thickness (1 for padding)
@@ -66,12 +66,13 @@ __global__ void __launch_bounds__(128, 2) k_lite_warp(const __grid_constant__ De
         stage_layer_consts(P, col, lcw, lane);
         __syncwarp();
 
-        double H[CPL], H0[CPL], T[CPL];
+        double H[CPL], H0[CPL], T[CPL], W[CPL];
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
             int i = lane * CPL + j;
             H[j] = (i < N) ? P.u[(size_t)i * M + col] : 0.0;
             T[j] = H[j] / P.ch_w;
+            W[j] = 0.0;
         }
         double t = P.t[col], dt = P.dt[col];
         const double nf = P.nf[col], nt = P.nt[col], toff = P.top_offset[col];
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(128, 2) k_lite_warp(const __grid_constant__ De
                 for (int j = 0; j < CPL; ++j) {
                     double thw, C, dth;
                     freezethaw_cell<MODE>(P, lcw + loff[j], H[j], dC, dK, T[j], thw, C, dHdT[j], dth, kc[j]);
+                    if (saveW) W[j] = thw;
                 }
                 // ---- kd = k_edge/dxc on the upper edge of every local cell (harmonic mean, math.jl:141)
                 double kup = __shfl_up_sync(FULL, kc[CPL - 1], 1);
@@ -222,7 +224,13 @@ __global__ void __launch_bounds__(128, 2) k_lite_warp(const __grid_constant__ De
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
             int i = lane * CPL + j;
-            if (i < N) P.u[(size_t)i * M + col] = H[j];
+            if (i < N) {
+                P.u[(size_t)i * M + col] = H[j];
+                // saved diagnostics = cache of the LAST tile evaluation (start of the last Picard iteration), as the
+                // reference saves them (problem.jl:67-68, Numerics/statevars.jl:81-106, cglite_step.jl:45-62)
+                if (saveT && nsteps > 0) saveT[(size_t)i * M + col] = T[j];
+                if (saveW && nsteps > 0) saveW[(size_t)i * M + col] = W[j];
+            }
         }
         if (lane == 0) {
             P.t[col] = t; P.dt[col] = dt; P.steps[col] += nsteps; P.iters[col] += niter;
@@ -233,11 +241,11 @@ __global__ void __launch_bounds__(128, 2) k_lite_warp(const __grid_constant__ De
 
 } // namespace cgb
 
-template <int CPL, int MODE>
-static int lite_warp_launch_m(cgb_handle* h, double t_target)
+template <int CPL, int MODE, int MINB>
+static int lite_warp_launch_b(cgb_handle* h, double t_target, double* saveT, double* saveW)
 {
     using namespace cgb;
-    auto kern = k_lite_warp<CPL, MODE>;
+    auto kern = k_lite_warp<CPL, MODE, MINB>;
     size_t smem = (size_t)(5 * CPL * 32 + 4 * h->nl * LC_STRIDE) * sizeof(double);
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
@@ -247,33 +255,40 @@ static int lite_warp_launch_m(cgb_handle* h, double t_target)
     }
     long long grid = std::min<long long>((h->M + 3) / 4, (long long)h->num_sms * blocks_per_sm);
     CUDA_TRY(h, cudaMemsetAsync(h->dev.counter, 0, sizeof(unsigned long long), h->stream));
-    kern<<<(unsigned)grid, 128, smem, h->stream>>>(h->dev, t_target);
+    kern<<<(unsigned)grid, 128, smem, h->stream>>>(h->dev, t_target, saveT, saveW);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return CGB_OK;
 }
 
+// register budget: 2 resident CTAs (x4 warps) per SM -- MINB = 3 and 4 spill and were 8 % / 13 % slower on B200
+template <int CPL, int MODE>
+static int lite_warp_launch_m(cgb_handle* h, double t_target, double* saveT, double* saveW)
+{
+    return lite_warp_launch_b<CPL, MODE, 2>(h, t_target, saveT, saveW);
+}
+
 template <int CPL>
-static int lite_warp_launch_t(cgb_handle* h, double t_target)
+static int lite_warp_launch_t(cgb_handle* h, double t_target, double* saveT, double* saveW)
 {
     bool fw = true;
     for (int l = 0; l < h->nl; ++l) fw &= h->fc_kind[l] == CGB_FC_FREEWATER;
-    return fw ? lite_warp_launch_m<CPL, 3>(h, t_target) : lite_warp_launch_m<CPL, 0>(h, t_target);
+    return fw ? lite_warp_launch_m<CPL, 3>(h, t_target, saveT, saveW) : lite_warp_launch_m<CPL, 0>(h, t_target, saveT, saveW);
 }
 
-static int lite_warp_launch(cgb_handle* h, double t_target)
+static int lite_warp_launch(cgb_handle* h, double t_target, double* saveT, double* saveW)
 {
     int cpl = (h->N + 31) / 32;
     switch (cpl) {
-    case 1: return lite_warp_launch_t<1>(h, t_target);
-    case 2: return lite_warp_launch_t<2>(h, t_target);
-    case 3: case 4: return lite_warp_launch_t<4>(h, t_target);
-    case 5: case 6: return lite_warp_launch_t<6>(h, t_target);
-    case 7: return lite_warp_launch_t<7>(h, t_target);
-    case 8: return lite_warp_launch_t<8>(h, t_target);
-    case 9: return lite_warp_launch_t<9>(h, t_target);
-    case 10: return lite_warp_launch_t<10>(h, t_target);
-    case 11: case 12: return lite_warp_launch_t<12>(h, t_target);
-    default: return lite_warp_launch_t<16>(h, t_target);
+    case 1: return lite_warp_launch_t<1>(h, t_target, saveT, saveW);
+    case 2: return lite_warp_launch_t<2>(h, t_target, saveT, saveW);
+    case 3: case 4: return lite_warp_launch_t<4>(h, t_target, saveT, saveW);
+    case 5: case 6: return lite_warp_launch_t<6>(h, t_target, saveT, saveW);
+    case 7: return lite_warp_launch_t<7>(h, t_target, saveT, saveW);
+    case 8: return lite_warp_launch_t<8>(h, t_target, saveT, saveW);
+    case 9: return lite_warp_launch_t<9>(h, t_target, saveT, saveW);
+    case 10: return lite_warp_launch_t<10>(h, t_target, saveT, saveW);
+    case 11: case 12: return lite_warp_launch_t<12>(h, t_target, saveT, saveW);
+    default: return lite_warp_launch_t<16>(h, t_target, saveT, saveW);
     }
 }

@@ -1,0 +1,53 @@
+// cgb_tu_fast.cu -- launcher of the FreeWater fast kernel (cgb_euler_fast.cuh).
+#include "cgb_launch.h"
+#include "cgb_euler_fast.cuh"
+using namespace cgb;
+
+// Tuned on B200 (profiles/): 3 resident CTAs per SM (168 registers, no spills) and the cubic reciprocal
+// were the fastest of MINB in {2,3,4} x {two Newton steps, one cubic step}.
+constexpr int kFastMinB = 3;
+constexpr bool kFastCubic = true;
+
+template <int CPL, bool SAVE>
+static int launch_fast_s(cgb_handle* h, double t_target, double* saveT, double* saveW)
+{
+    auto kern = k_heat_euler_fast<CPL, kFastMinB, kFastCubic, SAVE>;
+    size_t smem = (size_t)(4 * h->nl * FC_STRIDE) * sizeof(double);
+    static int blocks_per_sm = 0;   // per instantiation
+    if (blocks_per_sm == 0) {
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, 128, smem));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    long long tiles = (h->M + 3) / 4;
+    long long grid = std::min<long long>(tiles, (long long)h->num_sms * blocks_per_sm);
+    CUDA_TRY(h, cudaMemsetAsync(h->dev.counter, 0, sizeof(unsigned long long), h->stream));
+    kern<<<(unsigned)grid, 128, smem, h->stream>>>(h->dev, t_target, saveT, saveW);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return CGB_OK;
+}
+
+template <int CPL>
+static int launch_fast_t(cgb_handle* h, double t_target, double* saveT, double* saveW)
+{
+    // the saving instantiation is separate so that the plain stepping kernel carries no extra registers or branches
+    if (saveT || saveW) return launch_fast_s<CPL, true>(h, t_target, saveT, saveW);
+    return launch_fast_s<CPL, false>(h, t_target, nullptr, nullptr);
+}
+
+int cgb_launch_fast(cgb_handle* h, double t_target, double* saveT, double* saveW)
+{
+    int cpl = (h->N + 31) / 32;
+    switch (cpl) {
+    case 1: return launch_fast_t<1>(h, t_target, saveT, saveW);
+    case 2: return launch_fast_t<2>(h, t_target, saveT, saveW);
+    case 3: case 4: return launch_fast_t<4>(h, t_target, saveT, saveW);
+    case 5: case 6: return launch_fast_t<6>(h, t_target, saveT, saveW);
+    case 7: return launch_fast_t<7>(h, t_target, saveT, saveW);
+    case 8: return launch_fast_t<8>(h, t_target, saveT, saveW);
+    case 9: return launch_fast_t<9>(h, t_target, saveT, saveW);
+    case 10: return launch_fast_t<10>(h, t_target, saveT, saveW);
+    case 11: case 12: return launch_fast_t<12>(h, t_target, saveT, saveW);
+    default: return launch_fast_t<16>(h, t_target, saveT, saveW);
+    }
+}

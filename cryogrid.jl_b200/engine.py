@@ -6,6 +6,12 @@ import numpy as np
 from . import _lib as L
 
 
+# Saved-variable names.  "T"/"θw" follow the reference verbatim: its savefunc returns the diagnostic CACHE of the last RHS
+# evaluation, i.e. the state one step before the saved H (include/cgb200.h, cgb_solve_saveat); "*_now" are recomputed from
+# the saved state itself.
+SAVE_NAMES = {"T": "T", "H": "H", "θw": "thw", "thw": "thw", "T_now": "T_now", "θw_now": "thw_now", "thw_now": "thw_now"}
+
+
 class _EngineBase:
     """Methods shared by the heat and heat+salt engines (everything that does not depend on the state shape)."""
 
@@ -184,7 +190,7 @@ class Engine(_EngineBase):
 
     def solve_saveat(self, tsave, savevars=("T",), out=None):
         tsave = L.as_f64(tsave)
-        names = {"T": "T", "H": "H", "θw": "thw", "thw": "thw"}
+        names = SAVE_NAMES
         vars_c = ",".join(names[v] for v in savevars)
         shape = (tsave.size, len(savevars), self.N, self.M)
         if out is None:
@@ -197,7 +203,7 @@ class Engine(_EngineBase):
         """Device-side output path: keep only the cells `cells` of every saved variable (out[nsave, nvars, nsel, M]) and,
         optionally, the sub-grid thaw depth per column and save (thaw[nsave, M])."""
         tsave = L.as_f64(tsave)
-        names = {"T": "T", "H": "H", "θw": "thw", "thw": "thw"}
+        names = SAVE_NAMES
         cells = np.ascontiguousarray(cells, dtype=np.int32)
         vars_c = ",".join(names[v] for v in savevars) if cells.size else "T"
         shape = (tsave.size, len(savevars), cells.size, self.M)

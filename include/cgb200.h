@@ -179,8 +179,14 @@ int cgb_synchronize(cgb_handle* h);
 int cgb_get_diag(cgb_handle* h, const char* var, double t, double* out);
 /* solve(prob; saveat): advance through tsave[0..nsave) and write the saved variables
  * out[((s*nvars + v)*N + cell)*M + col] (savefunc/saveat!: problem.jl:67-68, integrator.jl:111-132).
- * vars: comma-separated subset of "H,T,thw".  out is a HOST pointer (pinned or pageable); copies are
- * overlapped with stepping on a second stream. */
+ * vars: comma-separated subset of "H,T,thw,T_now,thw_now".  out is a HOST pointer (pinned or pageable); copies are
+ * overlapped with stepping on a second stream.
+ * REFERENCE-VERBATIM SEMANTICS of the diagnostic variables T and thw: CryoGrid.jl's savefunc returns the *cached* diagnostic
+ * arrays of the last RHS evaluation (getvars -> retrieve, Numerics/statevars.jl:60-106), and CGEuler evaluates the tile
+ * BEFORE it applies u += dt*du (basic_solvers.jl:61-66); LiteImplicit's last evaluation is the start of its last Picard
+ * iteration (cglite_step.jl:45-62).  So the reference's saved T, θw belong to the state one step (one iteration) before the
+ * saved H.  "T"/"thw" reproduce exactly that (the stepping kernel writes them on the last step of each interval, no extra
+ * launch); "T_now"/"thw_now" are recomputed from the saved state itself; "H" is the prognostic state at the save time. */
 int cgb_solve_saveat(cgb_handle* h, const double* tsave, int64_t nsave, const char* vars, double* out);
 
 /* Device-side output path: like cgb_solve_saveat, but only the cells cell_index[0..nsel) are kept --

@@ -239,19 +239,31 @@ def test_idempotent_and_checkpoint(orc):
 def test_solve_saveat_matches_stepwise(orc):
     tile = common.samoylov_freew_tile(ncolumns=9, seed=6)
     H0 = cg.initialcondition(tile)
-    prob = cg.CryoGridProblem(tile, H0, (0.0, 5 * 86400.0), saveat=86400.0, savevars=("T", "H", "θw"))
-    sol = cg.solve(prob, cg.CGEuler())
+    prob = cg.CryoGridProblem(tile, H0, (0.0, 5 * 86400.0), saveat=86400.0, savevars=("T", "H", "θw", "T_now", "θw_now"))
+    sol = cg.solve(prob, cg.CGEuler(), dtmax=600.0)
     out = cg.CryoGridOutput(sol)
     assert out.T.shape == (6, tile.grid.ncells, 9) and sol.retcode == "Success"
-    eng = cg.Engine(tile)
+    eng = cg.Engine(tile, dtmax=600.0)
     eng.set_state(H0, 0.0)
     np.testing.assert_array_equal(out.H[0], H0)
+    np.testing.assert_array_equal(out.T[0], out.vars["T_now"][0])          # initial save: the cache IS the state
     for s in range(1, 6):
         eng.advance_to(s * 86400.0)
         np.testing.assert_array_equal(out.H[s], eng.get_state())
-        np.testing.assert_array_equal(out.T[s], eng.diag("T", s * 86400.0))
-        np.testing.assert_array_equal(out.vars["θw"][s], eng.diag("thw", s * 86400.0))
+        np.testing.assert_array_equal(out.vars["T_now"][s], eng.diag("T", s * 86400.0))
+        np.testing.assert_array_equal(out.vars["θw_now"][s], eng.diag("thw", s * 86400.0))
     eng.close()
+    # "T"/"θw" are what the reference saves: the diagnostic cache of the last RHS evaluation, one step behind H
+    # (Numerics/statevars.jl:60-106, basic_solvers.jl:61-66) -- exactly what the oracle's work arrays hold after an advance
+    for c in (0, 4, 8):
+        oc = orc.OracleColumn(tile, c)
+        Hr, tr, dtr = H0[:, c].copy(), 0.0, 60.0
+        for s in range(1, 6):
+            Hr, tr, dtr, _, _ = oc.advance(Hr, tr, dtr, s * 86400.0, dtmax=600.0)
+            assert np.max(np.abs(out.T[s][:, c] - oc.work.get("T"))) <= T_TOL
+            assert np.max(np.abs(out.vars["θw"][s][:, c] - oc.work.get("thw"))) <= THW_TOL
+            np.testing.assert_allclose(out.H[s][:, c], Hr, rtol=1e-12, atol=1e-3)
+    assert np.max(np.abs(out.T[3] - out.vars["T_now"][3])) > 1e-9                # ... and it does differ from T(H saved)
 
 
 def test_energy_conservation_large_batch():

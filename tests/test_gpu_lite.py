@@ -167,3 +167,20 @@ def test_device_steadystate_init(orc):
     eng.advance_to(86400.0)
     assert not eng.status()[0].any()
     eng.close()
+
+
+def test_lite_saved_diagnostics_follow_reference_cache(orc, variant):
+    # saved T/θw = cache of the last tile evaluation (start of the last Picard iteration), cglite_step.jl:45-62
+    tile = common.lite_ensemble_tile(ncolumns=5, seed=11)
+    H0 = cg.initialcondition(tile)
+    prob = cg.CryoGridProblem(tile, H0, (0.0, 20 * 86400.0), saveat=86400.0, savevars=("T", "θw", "H"))
+    sol = cg.solve(prob, cg.LiteImplicitEuler())
+    out = cg.CryoGridOutput(sol)
+    for c in range(tile.M):
+        oc = orc.OracleColumn(tile, c)
+        Hr, tr, dtr = H0[:, c].copy(), 0.0, 86400.0
+        for s in range(1, 21):
+            Hr, tr, dtr, *_ = oc.lite_advance(Hr, tr, dtr, s * 86400.0)
+            assert np.max(np.abs(out.T[s][:, c] - oc.work.get("T"))) <= 1e-6
+            assert np.max(np.abs(out.vars["θw"][s][:, c] - oc.work.get("thw"))) <= 1e-8
+            np.testing.assert_allclose(out.H[s][:, c], Hr, rtol=1e-10, atol=1e-2)
