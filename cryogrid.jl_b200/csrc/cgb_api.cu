@@ -565,6 +565,12 @@ static int launch_advance(cgb_handle* h, double t_target, double* saveT = nullpt
     return rc;
 }
 
+static bool fast_path(const cgb_handle* h)
+{
+    return h->cfg.physics == CGB_PHYSICS_HEAT && h->cfg.stepper == CGB_STEPPER_EULER && all_freewater(h) &&
+           h->cfg.limiter == CGB_LIMITER_MAXDELTA && h->fast_ok;
+}
+
 static int launch_advance_inner(cgb_handle* h, double t_target, double* saveT, double* saveW)
 {
     Diag D{};
@@ -725,6 +731,47 @@ extern "C" int cgb_solve_saveat(cgb_handle* h, const double* tsave, int64_t nsav
             if (e != cudaSuccess) CGB_FAIL(h, CGB_ERR_ALLOC, "staging buffer: %s", cudaGetErrorString(e));
         }
         h->stage_elems = per_save;
+    }
+    // Device-side saveat for the FreeWater fast path: up to `chunk` save times per launch -- a column is carried through all
+    // of them in registers, the saved fields of the chunk land contiguously in one staging buffer and leave in one copy.
+    bool chunked = fast_path(h) && !sv.Tnow && !sv.Wnow;
+    for (auto& n : sv.names) chunked = chunked && n != "H";   // H is the live state: it must be copied out after every save
+    for (int64_t s = 1; chunked && s < nsave; ++s) chunked = tsave[s] > tsave[s - 1];
+    if (chunked && nsave >= 2 && tsave[0] > h->t_front) {
+        const int chunk = (int)std::min<int64_t>(std::min<int64_t>(8, cgb_fast_max_targets()), nsave);
+        if (h->stage_elems < per_save * chunk) {
+            for (int i = 0; i < 2; ++i) {
+                if (h->d_stage[i]) cudaFree(h->d_stage[i]);
+                h->d_stage[i] = nullptr;
+                cudaError_t e = cudaMalloc((void**)&h->d_stage[i], per_save * chunk * sizeof(double));
+                if (e != cudaSuccess) CGB_FAIL(h, CGB_ERR_ALLOC, "staging buffer: %s", cudaGetErrorString(e));
+            }
+            h->stage_elems = per_save * chunk;
+        }
+        int64_t c = 0;
+        for (int64_t s0 = 0; s0 < nsave; ++c) {
+            // chunks shrink towards the end so that the last (un-overlapped) device-to-host copy is a single save
+            int n = (int)std::min<int64_t>(chunk, std::max<int64_t>(1, (nsave - s0 + 1) / 2)), b = (int)(c & 1);
+            if (c >= 2) CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->stage_free[b], 0));
+            double *bT = nullptr, *bW = nullptr;
+            for (size_t v = 0; v < sv.names.size(); ++v) {
+                if (sv.names[v] == "T") bT = h->d_stage[b] + v * NM; else bW = h->d_stage[b] + v * NM;
+            }
+            cudaEvent_t pa = nullptr, pb = nullptr;
+            if (h->profiling) { cudaEventCreate(&pa); cudaEventCreate(&pb); cudaEventRecord(pa, h->stream); }
+            rc = cgb_launch_fast_multi(h, tsave + s0, n, bT, bW, (long long)per_save);
+            if (h->profiling) { cudaEventRecord(pb, h->stream); h->prof_events.emplace_back(pa, pb); }
+            if (rc) return rc;
+            h->t_front = tsave[s0 + n - 1];
+            CUDA_TRY(h, cudaEventRecord(h->stage_ready[b], h->stream));
+            CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->stage_ready[b], 0));
+            CUDA_TRY(h, cudaMemcpyAsync(out + (size_t)s0 * per_save, h->d_stage[b], (size_t)n * per_save * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+            CUDA_TRY(h, cudaEventRecord(h->stage_free[b], h->copy_stream));
+            s0 += n;
+        }
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+        return CGB_OK;
     }
     for (int64_t s = 0; s < nsave; ++s) {
         int b = (int)(s & 1);

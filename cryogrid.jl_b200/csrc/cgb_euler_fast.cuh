@@ -31,8 +31,18 @@ __device__ __forceinline__ double warp_max_nonneg(double v)
 template <bool CUBIC>
 __device__ __forceinline__ double rcp_sel(double a) { return CUBIC ? rcp_fast3(a) : rcp_fast(a); }
 
+// Save times of one launch, passed by value: a column is advanced through all of them without leaving its warp, and the
+// diagnostics to be saved at target k go to saveT/saveW + k*save_stride (device-side saveat).
+constexpr int FAST_MAX_TARGETS = 16;
+struct FastTargets {
+    double t[FAST_MAX_TARGETS];
+    int n;
+    long long save_stride;   // elements between consecutive saves in saveT / saveW
+};
+
 template <int CPL, int MINB, bool CUBIC, bool SAVE>
-__global__ void __launch_bounds__(128, MINB) k_heat_euler_fast(const __grid_constant__ Dev P, double t_target, double* __restrict__ saveT, double* __restrict__ saveW)
+__global__ void __launch_bounds__(128, MINB) k_heat_euler_fast(const __grid_constant__ Dev P, const __grid_constant__ FastTargets TG,
+                                                                double* __restrict__ saveT, double* __restrict__ saveW)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31;
@@ -163,6 +173,8 @@ __global__ void __launch_bounds__(128, MINB) k_heat_euler_fast(const __grid_cons
         // the warp reduction and the reciprocal of step n's limiter are in flight -- they do not depend on dt_{n+1}.
         double vtop = top_value(t);
         stage_a();
+        for (int kt = 0; kt < TG.n; ++kt) {
+        const double t_target = TG.t[kt];
         while (t < t_target) {
             if (fkind == 2 && (t < ft_first || t > ft_last)) { status |= 4; break; }     // providers.jl:30-33
             if (SAVE && !(t + dt < t_target)) {
@@ -173,11 +185,12 @@ __global__ void __launch_bounds__(128, MINB) k_heat_euler_fast(const __grid_cons
                 for (int j = 0; j < CPL; ++j) {
                     int i = lane * CPL + j;
                     if (i < N) {
-                        if (saveT) saveT[(size_t)i * M + col] = T[j];
+                        size_t o = (size_t)kt * TG.save_stride + (size_t)i * M + col;
+                        if (saveT) saveT[o] = T[j];
                         if (saveW) {
                             const double* c = lcw + loff[j];
                             double hc = sel_min(relu_bits(H[j]), c[FC_LTH]);
-                            saveW[(size_t)i * M + col] = (hc * c[FC_INVLTH]) * c[FC_THWI];
+                            saveW[o] = (hc * c[FC_INVLTH]) * c[FC_THWI];
                         }
                     }
                 }
@@ -231,6 +244,8 @@ __global__ void __launch_bounds__(128, MINB) k_heat_euler_fast(const __grid_cons
             double rem = t_target - tn;
             dt = (rem > 0.0) ? sel_min(dtn, rem) : dtn;                              // integrator.jl:126-131 (:89 is implied)
             t = tn;
+        }
+        if (status) break;
         }
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {

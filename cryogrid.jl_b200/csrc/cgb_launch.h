@@ -3,6 +3,8 @@
 #include "cgb_handle.h"
 
 int cgb_launch_fast(cgb_handle* h, double t_target, double* saveT, double* saveW);                 // cgb_tu_fast.cu
+int cgb_launch_fast_multi(cgb_handle* h, const double* targets, int n, double* saveT, double* saveW, long long save_stride);
+int cgb_fast_max_targets(void);
 int cgb_launch_euler(cgb_handle* h, int mode, bool diag, double t_target, const cgb::Diag& D);     // cgb_tu_euler.cu
 int cgb_launch_euler_step(cgb_handle* h, int mode, double t_target, const cgb::Diag& D);
 int cgb_launch_euler_diag(cgb_handle* h, double t, const cgb::Diag& D);                            // cgb_tu_euler_diag.cu

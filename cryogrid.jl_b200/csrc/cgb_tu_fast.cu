@@ -9,7 +9,7 @@ constexpr int kFastMinB = 3;
 constexpr bool kFastCubic = true;
 
 template <int CPL, bool SAVE>
-static int launch_fast_s(cgb_handle* h, double t_target, double* saveT, double* saveW)
+static int launch_fast_s(cgb_handle* h, const FastTargets& tg, double* saveT, double* saveW)
 {
     auto kern = k_heat_euler_fast<CPL, kFastMinB, kFastCubic, SAVE>;
     size_t smem = (size_t)(4 * h->nl * FC_STRIDE) * sizeof(double);
@@ -21,33 +21,45 @@ static int launch_fast_s(cgb_handle* h, double t_target, double* saveT, double* 
     long long tiles = (h->M + 3) / 4;
     long long grid = std::min<long long>(tiles, (long long)h->num_sms * blocks_per_sm);
     CUDA_TRY(h, cudaMemsetAsync(h->dev.counter, 0, sizeof(unsigned long long), h->stream));
-    kern<<<(unsigned)grid, 128, smem, h->stream>>>(h->dev, t_target, saveT, saveW);
+    kern<<<(unsigned)grid, 128, smem, h->stream>>>(h->dev, tg, saveT, saveW);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return CGB_OK;
 }
 
 template <int CPL>
-static int launch_fast_t(cgb_handle* h, double t_target, double* saveT, double* saveW)
+static int launch_fast_t(cgb_handle* h, const FastTargets& tg, double* saveT, double* saveW)
 {
     // the saving instantiation is separate so that the plain stepping kernel carries no extra registers or branches
-    if (saveT || saveW) return launch_fast_s<CPL, true>(h, t_target, saveT, saveW);
-    return launch_fast_s<CPL, false>(h, t_target, nullptr, nullptr);
+    if (saveT || saveW) return launch_fast_s<CPL, true>(h, tg, saveT, saveW);
+    return launch_fast_s<CPL, false>(h, tg, nullptr, nullptr);
 }
 
 int cgb_launch_fast(cgb_handle* h, double t_target, double* saveT, double* saveW)
 {
+    return cgb_launch_fast_multi(h, &t_target, 1, saveT, saveW, 0);
+}
+
+int cgb_fast_max_targets(void) { return FAST_MAX_TARGETS; }
+
+int cgb_launch_fast_multi(cgb_handle* h, const double* targets, int n, double* saveT, double* saveW, long long save_stride)
+{
+    if (n < 1 || n > FAST_MAX_TARGETS) CGB_FAIL(h, CGB_ERR_INVALID, "cgb_launch_fast_multi: 1..%d targets", FAST_MAX_TARGETS);
+    FastTargets tg{};
+    for (int k = 0; k < n; ++k) tg.t[k] = targets[k];
+    tg.n = n; tg.save_stride = save_stride;
+    const double t_target = 0.0; (void)t_target;
     int cpl = (h->N + 31) / 32;
     switch (cpl) {
-    case 1: return launch_fast_t<1>(h, t_target, saveT, saveW);
-    case 2: return launch_fast_t<2>(h, t_target, saveT, saveW);
-    case 3: case 4: return launch_fast_t<4>(h, t_target, saveT, saveW);
-    case 5: case 6: return launch_fast_t<6>(h, t_target, saveT, saveW);
-    case 7: return launch_fast_t<7>(h, t_target, saveT, saveW);
-    case 8: return launch_fast_t<8>(h, t_target, saveT, saveW);
-    case 9: return launch_fast_t<9>(h, t_target, saveT, saveW);
-    case 10: return launch_fast_t<10>(h, t_target, saveT, saveW);
-    case 11: case 12: return launch_fast_t<12>(h, t_target, saveT, saveW);
-    default: return launch_fast_t<16>(h, t_target, saveT, saveW);
+    case 1: return launch_fast_t<1>(h, tg, saveT, saveW);
+    case 2: return launch_fast_t<2>(h, tg, saveT, saveW);
+    case 3: case 4: return launch_fast_t<4>(h, tg, saveT, saveW);
+    case 5: case 6: return launch_fast_t<6>(h, tg, saveT, saveW);
+    case 7: return launch_fast_t<7>(h, tg, saveT, saveW);
+    case 8: return launch_fast_t<8>(h, tg, saveT, saveW);
+    case 9: return launch_fast_t<9>(h, tg, saveT, saveW);
+    case 10: return launch_fast_t<10>(h, tg, saveT, saveW);
+    case 11: case 12: return launch_fast_t<12>(h, tg, saveT, saveW);
+    default: return launch_fast_t<16>(h, tg, saveT, saveW);
     }
 }

@@ -182,9 +182,11 @@ class Engine(_EngineBase):
         self._check(self.lib.cgb_rhs(self.h, float(t), L.dptr(du)))
         return du
 
-    def diag(self, var, t):
+    def diag(self, var, t, out=None):
         n = self.N + 1 if var in ("k", "jH") else self.N
-        out = np.empty((n, self.M))
+        if out is None:
+            out = np.empty((n, self.M))
+        assert out.shape == (n, self.M) and out.flags.c_contiguous and out.dtype == np.float64
         self._check(self.lib.cgb_get_diag(self.h, var.encode(), float(t), L.dptr(out)))
         return out
 

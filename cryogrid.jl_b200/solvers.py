@@ -54,7 +54,10 @@ def solve(prob, alg=None, dt=None, dtmax=None, dtmin=1.0, device=0, engine=None,
     first = 0
     if saves.size and saves[0] == t0:           # initial save: basic_solvers.jl:33-37
         for v, name in enumerate(savevars):
-            out[0, v] = eng.get_state() if name == "H" else eng.diag({"θw": "thw", "T_now": "T", "θw_now": "thw", "thw_now": "thw"}.get(name, name), t0)
+            if name == "H":
+                out[0, v] = prob.u0
+            else:   # written straight into the (possibly pinned) output buffer
+                eng.diag({"θw": "thw", "T_now": "T", "θw_now": "thw", "thw_now": "thw"}.get(name, name), t0, out=out[0, v])
         first = 1
     if saves.size > first:
         eng.solve_saveat(saves[first:], savevars, out=out[first:])
