@@ -8,7 +8,7 @@ from .grids import (Grid, DefaultGrid_1cm, DefaultGrid_2cm, DefaultGrid_5cm, Def
                     DefaultGrid_50cm, DefaultGrid_1m)
 from .hostmath import ThermalProperties
 from .model import (FreeWater, VanGenuchten, DallAmico, PainterKarra, DallAmicoSalt, SFCCPreSolver, SFCCNewtonSolver,
-                    SimpleSoil, Profile, SoilProfile, TemperatureProfile, Input, Interpolated1D, NFactor, TemperatureBC,
+                    SimpleSoil, Heterogeneous, Profile, SoilProfile, TemperatureProfile, Input, Interpolated1D, NFactor, TemperatureBC,
                     ConstantBC, PeriodicBC, ConstantTemperature, ConstantFlux, GeothermalHeatFlux, MaxDelta, CFL,
                     HeatBalance, EnthalpyImplicit, Ground, Top, Bottom, Stratigraphy, ThermalSteadyStateInit, initializer,
                     Tile, SoilHeatTile, initialcondition, Dirichlet, Neumann)

@@ -18,8 +18,8 @@ extern "C" int cgb_create(const cgb_config* cfg, cgb_handle** out)
     if (!cfg || !out) { g_create_error = "null argument"; return CGB_ERR_INVALID; }
     *out = nullptr;
     if (cfg->abi_version != CGB_ABI_VERSION) { g_create_error = "ABI version mismatch"; return CGB_ERR_INVALID; }
-    if (cfg->n_cells < 2 || cfg->n_columns < 1 || cfg->n_layers < 1 || cfg->n_layers > 64) {
-        g_create_error = "need n_cells >= 2, n_columns >= 1, 1 <= n_layers <= 64";
+    if (cfg->n_cells < 2 || cfg->n_columns < 1 || cfg->n_layers < 1 || cfg->n_layers > cfg->n_cells) {
+        g_create_error = "need n_cells >= 2, n_columns >= 1, 1 <= n_layers <= n_cells (n_layers == n_cells: Heterogeneous per-cell parameters)";
         return CGB_ERR_INVALID;
     }
     int ndev = 0;

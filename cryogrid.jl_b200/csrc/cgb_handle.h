@@ -95,6 +95,21 @@ static int dev_alloc(cgb_handle* h, T** p, size_t n)
     return CGB_OK;
 }
 
+// Opts the kernel into large dynamic shared memory when needed (per-cell "Heterogeneous" parameter blocks) and returns the
+// number of resident CTAs per SM for this launch configuration.
+static inline cudaError_t cgb_prepare_kernel(cgb_handle* h, const void* kern, size_t smem, int* blocks_per_sm)
+{
+    (void)h;
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, 128, smem);
+    if (e == cudaSuccess && *blocks_per_sm < 1) *blocks_per_sm = 1;
+    return e;
+}
+
 template <typename T>
 static int dev_upload(cgb_handle* h, T** p, const std::vector<T>& v)
 {

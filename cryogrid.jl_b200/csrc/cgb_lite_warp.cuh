@@ -247,12 +247,8 @@ static int lite_warp_launch_b(cgb_handle* h, double t_target, double* saveT, dou
     using namespace cgb;
     auto kern = k_lite_warp<CPL, MODE, MINB>;
     size_t smem = (size_t)(5 * CPL * 32 + 4 * h->nl * LC_STRIDE) * sizeof(double);
-    static int blocks_per_sm = 0;
-    if (blocks_per_sm == 0) {
-        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, 128, smem));
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
-    }
+    int blocks_per_sm = 0;
+    CUDA_TRY(h, cgb_prepare_kernel(h, (const void*)kern, smem, &blocks_per_sm));
     long long grid = std::min<long long>((h->M + 3) / 4, (long long)h->num_sms * blocks_per_sm);
     CUDA_TRY(h, cudaMemsetAsync(h->dev.counter, 0, sizeof(unsigned long long), h->stream));
     kern<<<(unsigned)grid, 128, smem, h->stream>>>(h->dev, t_target, saveT, saveW);

@@ -9,12 +9,8 @@ static int launch_euler_t(cgb_handle* h, double t_target, const Diag& D)
 {
     auto kern = k_heat_euler<CPL, MODE, DIAG>;
     size_t smem = (size_t)(5 * CPL * 32 + 4 * h->nl * LC_STRIDE) * sizeof(double);
-    static int blocks_per_sm = 0;   // per instantiation
-    if (blocks_per_sm == 0) {
-        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, 128, smem));
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
-    }
+    int blocks_per_sm = 0;
+    CUDA_TRY(h, cgb_prepare_kernel(h, (const void*)kern, smem, &blocks_per_sm));
     long long tiles = (h->M + 3) / 4;
     long long grid = std::min<long long>(tiles, (long long)h->num_sms * blocks_per_sm);
     CUDA_TRY(h, cudaMemsetAsync(h->dev.counter, 0, sizeof(unsigned long long), h->stream));

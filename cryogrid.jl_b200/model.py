@@ -86,6 +86,14 @@ class SimpleSoil:
     freezecurve: Any = field(default_factory=FreeWater)
 
 
+@dataclass
+class Heterogeneous:
+    """Heterogeneous{SimpleSoil} (Soils/para/simple.jl:92-182): soil parameters vary from cell to cell; the reference
+    initialises the per-cell fields por/sat/org by interpolating the profile linearly in depth (InterpInitializer, flat
+    outside).  Use it as the `para` of a Ground layer; the Tile expands it to one parameter set per cell."""
+    profile: Any                  # SoilProfile((z, SimpleSoil(...)), ...)
+
+
 class Profile(list):
     """Ordered (depth, value) pairs."""
 
@@ -247,7 +255,8 @@ class Tile:
         self.strat, self.grid, self.inputs, self.inits = strat, grid, inputs, inits
         self.M = int(ncolumns)
         M, N = self.M, grid.ncells
-        layers = strat.layers
+        layers = self._expand_heterogeneous(strat.layers, grid, strat.z_bot, self.M)
+        self._layers = layers
         nl = len(layers)
         # layer -> cells (Numerics/grid.jl:49-58 subgridinds: boundaries snap to the grid edge <= z)
         starts = [int(np.clip(np.searchsorted(grid.edges, z, side="right") - 1, 0, N - 1)) for z, _ in layers]
@@ -285,6 +294,27 @@ class Tile:
         self.top_kind, self.top_forcing, self.use_nfactor, self.nf, self.nt, self.top_offset = self._top(strat.top.bc)
         self.bot_kind, self.bot_forcing, self.bot_value = self._bottom(strat.bottom.bc)
         self.tables = None   # built lazily: list of (Hk, Tk, extrap) + map [nl, M]
+
+    @staticmethod
+    def _expand_heterogeneous(layers, grid, z_bot, M):
+        out = []
+        for li, (z, g) in enumerate(layers):
+            if not isinstance(g.para, Heterogeneous):
+                out.append((z, g))
+                continue
+            z_end = layers[li + 1][0] if li + 1 < len(layers) else z_bot
+            prof = g.para.profile
+            zk = np.array([p[0] for p in prof], dtype=np.float64)
+            fc = prof[0][1].freezecurve
+            idx = np.nonzero((grid.edges[:-1] >= z - 1e-12) & (grid.edges[:-1] < z_end - 1e-12))[0]
+            for i in idx:
+                zc = grid.cells[i]
+                vals = {}
+                for name in ("por", "sat", "org"):
+                    vk = np.stack([_col(getattr(p[1], name), M) for p in prof])     # [nk, M]
+                    vals[name] = np.array([np.interp(zc, zk, vk[:, c]) for c in range(M)])
+                out.append((float(grid.edges[i]), Ground(SimpleSoil(freezecurve=fc, **vals), heat=g.heat, fcsolver=g.fcsolver)))
+        return out
 
     # -- boundary flattening
     def _forcing(self, src):

@@ -85,7 +85,7 @@ def test_too_many_cells_is_refused():
 
 
 def test_many_layers_and_single_column(orc):
-    tile = _tile(128, 1, nlayers=64, seed=3)           # the maximum number of layers, one column
+    tile = _tile(128, 1, nlayers=64, seed=3)           # many layers, one column
     H0 = cg.initialcondition(tile)
     eng = cg.Engine(tile, dtmax=30.0)
     eng.set_state(H0, 0.0)
@@ -111,3 +111,32 @@ def test_large_ragged_batch_is_deterministic():
         assert s["status_or"] == 0 and s["n_columns"] == M
         eng.close()
     np.testing.assert_array_equal(res[0], res[1])
+
+
+def test_heterogeneous_per_cell_parameters(orc):
+    # Heterogeneous{SimpleSoil} -- one parameter set per cell (n_layers == n_cells), explicit and implicit
+    grid = cg.DefaultGrid_20cm
+    prof = cg.SoilProfile((0.0, cg.SimpleSoil(por=np.array([0.8, 0.6]), org=0.7)), (1.0, cg.SimpleSoil(por=0.5, org=0.2)),
+                          (10.0, cg.SimpleSoil(por=0.3, org=0.0)), (1000.0, cg.SimpleSoil(por=0.05, org=0.0)))
+    for op, stepper in (("H", "euler"), ("implicit", "lite")):
+        heat = cg.HeatBalance(op=op)
+        strat = cg.Stratigraphy((0.0, cg.Top(cg.TemperatureBC(cg.PeriodicBC(cg.Dirichlet, common.YEAR, 15.0, 0.0, -5.0)))),
+                                [(0.0, cg.Ground(cg.Heterogeneous(prof), heat=heat))], (1000.0, cg.Bottom(cg.GeothermalHeatFlux(0.053))))
+        tile = cg.Tile(strat, grid, None, cg.initializer("T", cg.TemperatureProfile((0.0, -6.0), (1000.0, 10.0))), ncolumns=2)
+        assert tile.n_layers == grid.ncells and np.array_equal(tile.cell_layer, np.arange(grid.ncells))
+        assert tile.por[0, 0] == pytest.approx(np.interp(grid.cells[0], [0.0, 1.0], [0.8, 0.5]))
+        H0 = cg.initialcondition(tile)
+        eng = cg.Engine(tile, stepper=stepper)
+        eng.set_state(H0, 0.0)
+        tt = 5 * 86400.0
+        eng.advance_to(tt)
+        H = eng.get_state()
+        assert not eng.status()[0].any()
+        for c in range(2):
+            oc = orc.OracleColumn(tile, c)
+            if stepper == "euler":
+                Hr, *_ = oc.advance(H0[:, c], 0.0, 60.0, tt)
+            else:
+                Hr, *_ = oc.lite_advance(H0[:, c], 0.0, 86400.0, tt)
+            np.testing.assert_allclose(H[:, c], Hr, rtol=1e-9, atol=1e-2)
+        eng.close()
