@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libcgb200.so")
+LIB_PATH = os.environ.get("CGB_LIB_PATH") or os.path.join(HERE, "lib", "libcgb200.so")   # override: A/B builds only
 
 ABI_VERSION = 1
 OK = 0
@@ -82,6 +82,7 @@ SIGNATURES = {
     "cgb_profile_enable": (C.c_int, [_P, C.c_int32]),
     "cgb_profile_read": (C.c_int, [_P, _I64, C.POINTER(C.c_double)]),
     "cgb_selftest_rcp": (C.c_int, [_D, C.c_int64, _D, _D, _D]),
+    "cgb_selftest_explog": (C.c_int, [_D, C.c_int64, _D, _D]),
 }
 
 _lib = None

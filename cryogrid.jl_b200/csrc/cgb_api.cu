@@ -269,12 +269,7 @@ static int finalize(cgb_handle* h)
     int maxid = -1;
     for (auto& kv : h->tables) maxid = std::max(maxid, kv.first);
     std::vector<int> off(std::max(maxid + 1, 1), 0), len(std::max(maxid + 1, 1), 0), ext(std::max(maxid + 1, 1), 0);
-    std::vector<double> allH, allT;
-    for (auto& kv : h->tables) {
-        off[kv.first] = (int)allH.size(); len[kv.first] = (int)kv.second.H.size(); ext[kv.first] = kv.second.extrap;
-        allH.insert(allH.end(), kv.second.H.begin(), kv.second.H.end());
-        allT.insert(allT.end(), kv.second.T.begin(), kv.second.T.end());
-    }
+    for (auto& kv : h->tables) { len[kv.first] = (int)kv.second.H.size(); ext[kv.first] = kv.second.extrap; }
     if (any_lut) {
         for (int l = 0; l < h->nl; ++l) {
             if (h->fc_kind[l] == CGB_FC_FREEWATER || h->fc_solver[l] != CGB_SOLVER_LUT) continue;
@@ -288,35 +283,54 @@ static int finalize(cgb_handle* h)
             }
         }
     }
-    // segment slopes and the bucket acceleration index of every table (see lut_eval_bucket)
-    std::vector<double> allS(allH.size(), 0.0);
-    std::vector<int2> allB;
-    std::vector<int> boff(off.size(), 0), nit(off.size(), 1);
+    // knots (H, T, segment slope dT/dH as three arrays: neighbouring knots share 32-byte sectors, which is what the
+    // scattered per-lane loads of the kernels want) and the bucket acceleration index of every table (see
+    // lut_eval_bucket).  The uniform H-grid has nb = 2^k ~ 8x the knot count buckets (so that a bucket rarely holds more
+    // than one knot), bounded by LUT_NB_MAX and by a total index size of 256 MB when there are very many tables.  A
+    // bucket is one word: first candidate segment | trips << 24, the candidates being [lo, lo + 2^trips - 1]; every
+    // table is padded with +Inf knots so that this range never leaves it.
+    std::vector<double> allH, allT, allS;
+    std::vector<unsigned> allB;
+    std::vector<int> boff(off.size(), 0), nbs(off.size(), LUT_NB_MIN);
+    size_t nb_cap = LUT_NB_MAX;
+    while (nb_cap > (size_t)LUT_NB_MIN && nb_cap * sizeof(unsigned) * std::max<size_t>(h->tables.size(), 1) > ((size_t)256 << 20)) nb_cap >>= 1;
+    static const int nb_factor = getenv("CGB_LUT_NB_FACTOR") ? atoi(getenv("CGB_LUT_NB_FACTOR")) : 8;   // tuning knob
     for (auto& kv : h->tables) {
         const std::vector<double>& H = kv.second.H; const std::vector<double>& T = kv.second.T;
-        int nk = (int)H.size(), o = off[kv.first];
-        for (int i = 0; i + 1 < nk; ++i) allS[o + i] = (T[i + 1] - T[i]) / (H[i + 1] - H[i]);
-        allS[o + nk - 1] = allS[o + nk - 2];
+        const int nk = (int)H.size();
+        if (nk >= (1 << 24)) CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "SFCC table %d has %d knots (limit 2^24-1)", kv.first, nk);
+        int nb = LUT_NB_MIN;
+        while (nb < nb_factor * nk && nb < (int)nb_cap) nb <<= 1;
+        nbs[kv.first] = nb;
         boff[kv.first] = (int)allB.size();
-        double hmin = H[0], bw = (H[nk - 1] - H[0]) / LUT_NB;
-        int maxr = 1;
+        // the device computes the bucket as (int)((H - Hmin) * (nb / range)): three roundings, i.e. a slop of ~1e-15 range
+        // against the boundaries Hmin + b bw used here; widen every bucket by 1e-12 range
+        double hmin = H[0], range = H[nk - 1] - H[0], bw = range / nb, eps = 1e-12 * range;
         auto last_le = [&](double x) { return (int)(std::upper_bound(H.begin(), H.end(), x) - H.begin()) - 1; };
-        for (int b = 0; b < LUT_NB; ++b) {
-            int lo = std::max(last_le(hmin + b * bw) - 1, 0), hi = std::min(last_le(hmin + (b + 1) * bw) + 1, nk - 2);
-            lo = std::min(lo, nk - 2); hi = std::max(hi, lo);
-            allB.push_back(make_int2(lo, hi));
-            maxr = std::max(maxr, hi - lo + 1);
+        int tmax = 0;
+        for (int b = 0; b < nb; ++b) {
+            int lo = std::min(std::max(last_le(hmin + b * bw - eps), 0), nk - 1);
+            int hi = std::max(std::min(last_le(hmin + (b + 1) * bw + eps), nk - 1), lo);
+            int trips = 0;
+            while ((1 << trips) < hi - lo + 1) ++trips;
+            tmax = std::max(tmax, trips);
+            allB.push_back((unsigned)lo | ((unsigned)trips << 24));
         }
-        int it = 0; while ((1 << it) < maxr) ++it;
-        nit[kv.first] = it + 1;
+        off[kv.first] = (int)allH.size();
+        for (int i = 0; i < nk; ++i) {
+            int sgm = std::min(i, nk - 2);
+            allH.push_back(H[i]); allT.push_back(T[i]);
+            allS.push_back((T[sgm + 1] - T[sgm]) / (H[sgm + 1] - H[sgm]));          // knot nk-1: the last segment continued
+        }
+        for (int i = 0; i < (1 << tmax); ++i) { allH.push_back(INFINITY); allT.push_back(0.0); allS.push_back(0.0); }
     }
-    double *p_lh, *p_lt, *p_ls; int2* p_lb; int *p_off, *p_len, *p_ext, *p_boff, *p_nit, *p_map = nullptr;
+    double *p_lh, *p_lt, *p_ls; unsigned* p_lb; int *p_off, *p_len, *p_ext, *p_boff, *p_nb, *p_map = nullptr;
     rc |= dev_upload(h, &p_lh, allH); rc |= dev_upload(h, &p_lt, allT); rc |= dev_upload(h, &p_ls, allS); rc |= dev_upload(h, &p_lb, allB);
     rc |= dev_upload(h, &p_off, off); rc |= dev_upload(h, &p_len, len); rc |= dev_upload(h, &p_ext, ext);
-    rc |= dev_upload(h, &p_boff, boff); rc |= dev_upload(h, &p_nit, nit);
+    rc |= dev_upload(h, &p_boff, boff); rc |= dev_upload(h, &p_nb, nbs);
     if (!h->table_map.empty()) rc |= dev_upload(h, &p_map, h->table_map);
     d.lutH = p_lh; d.lutT = p_lt; d.lutS = p_ls; d.lutB = p_lb; d.lut_off = p_off; d.lut_len = p_len; d.lut_extrap = p_ext;
-    d.lut_boff = p_boff; d.lut_nit = p_nit; d.table_map = p_map;
+    d.lut_boff = p_boff; d.lut_nb = p_nb; d.table_map = p_map;
     // per (layer, column) parameters
     auto up_cl = [&](const char* name, const double** dst) {
         double* p; std::vector<double> v = expand(h, h->params[name], CGB_PER_COLUMN_LAYER);
@@ -1002,6 +1016,29 @@ extern "C" int cgb_selftest_rcp(const double* x, int64_t n, double* out_raw, dou
     cudaMemcpy(out_raw, d + n, n * sizeof(double), cudaMemcpyDeviceToHost);
     cudaMemcpy(out_newton2, d + 2 * n, n * sizeof(double), cudaMemcpyDeviceToHost);
     cudaMemcpy(out_cubic, d + 3 * n, n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return e == cudaSuccess ? CGB_OK : CGB_ERR_CUDA;
+}
+
+// self-test of the transcendental replacements used by the van Genuchten powers (tests/test_gpu_sfcc.py)
+__global__ void k_selftest_explog(const double* __restrict__ x, long long n, double* ex, double* lg)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) { ex[i] = exp_fast(x[i]); lg[i] = log_pos(fabs(x[i])); }
+}
+
+extern "C" int cgb_selftest_explog(const double* x, int64_t n, double* out_exp, double* out_log)
+{
+    if (!x || n < 1 || !out_exp || !out_log) return CGB_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return CGB_ERR_NO_DEVICE;
+    double* d = nullptr;
+    if (cudaMalloc((void**)&d, 3 * n * sizeof(double)) != cudaSuccess) return CGB_ERR_ALLOC;
+    cudaMemcpy(d, x, n * sizeof(double), cudaMemcpyHostToDevice);
+    k_selftest_explog<<<(unsigned)((n + 255) / 256), 256>>>(d, n, d + n, d + 2 * n);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(out_exp, d + n, n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaMemcpy(out_log, d + 2 * n, n * sizeof(double), cudaMemcpyDeviceToHost);
     cudaFree(d);
     return e == cudaSuccess ? CGB_OK : CGB_ERR_CUDA;
 }

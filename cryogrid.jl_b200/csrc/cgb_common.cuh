@@ -10,7 +10,7 @@ constexpr unsigned FULL = 0xffffffffu;
 
 // per-(column, layer) derived constants staged in shared memory (one block per warp)
 constexpr int LC_STRIDE = 24;
-constexpr int LUT_NB = 1024;   // uniform H-buckets per presolver table (acceleration index built on the host)
+constexpr int LUT_NB_MIN = 64, LUT_NB_MAX = 16384;   // uniform H-buckets per presolver table: power of two ~ 8x the knot count (host-built index)
 enum LayerConst {
     LC_THWI = 0,   // θwi = por*sat                        (Soils/para/simple.jl:19,87)
     LC_LTH,        // L*θwi                                 (heat_conduction.jl:40)
@@ -29,13 +29,13 @@ enum LayerConst {
     LC_CBS,        // sfccheatcap at θw = 0 (with the (1-θsat) quirk, soil_heat.jl:13-14)
     LC_KIND,       // int: freeze-curve kind | solver<<8
     LC_TABOFF,     // int2: LUT knot offset, LUT length
-    LC_TABLEN,     // int2: extrapolation mode, bisection iterations
+    LC_TABLEN,     // int2: extrapolation mode, unused
     LC_SAT,        // θwi/por
     LC_BOFF,       // int2: bucket-array offset, unused
     LC_HMIN,       // first knot
     LC_HMAX,       // last knot
-    LC_INVBW,      // LUT_NB / (Hmax - Hmin)
-    LC_SPARE
+    LC_INVBW,      // nb / (Hmax - Hmin)
+    LC_NBM1        // nb - 1 (as double: clamp bound of the bucket index)
 };
 
 struct Forcing {
@@ -64,9 +64,9 @@ struct Dev {
     const double *por, *sat, *org;                               // [n_layers*M]
     const double *vg_alpha, *vg_n, *theta_res, *Tm, *beta, *omega; // [n_layers*M]
     const int* table_map;     // [n_layers*M] or nullptr
-    const double* lutH; const double* lutT; const double* lutS;   // knots H, T and segment slopes dT/dH (concatenated tables)
-    const int2* lutB;         // per table LUT_NB buckets: [lo, hi] range of candidate segments (concatenated)
-    const int* lut_off; const int* lut_len; const int* lut_extrap; const int* lut_boff; const int* lut_nit;
+    const double* lutH; const double* lutT; const double* lutS;   // knots H, T and segment slopes dT/dH (concatenated, +Inf padded tables)
+    const unsigned* lutB;     // per table nb buckets: first candidate segment | trips << 24 (concatenated)
+    const int* lut_off; const int* lut_len; const int* lut_extrap; const int* lut_boff; const int* lut_nb;
     // thermal properties
     double sk_w, sk_i, sk_a, sk_m, sk_o;   // sqrt(kh_*)
     double ch_w, ch_i, ch_a, ch_m, ch_o, L;
@@ -166,6 +166,68 @@ __device__ __forceinline__ double relu_bits(double x)
     return __hiloint2double(hi & m, lo & m);
 }
 
+// exp(a) without the special-case handling of the CUDA math library (80 SASS instructions -> ~25): a is clamped to
+// [-708, 709] (results stay normal, so the power of two can be added straight into the exponent field), reduced by
+// k = rint(a log2 e) with a two-term ln 2, and evaluated with the degree-13 Taylor polynomial on |r| <= 0.3466
+// (truncation 4e-18).  Measured against libm in tests/test_gpu_sfcc.py: <= 1 ulp over [-700, 700].
+__device__ __forceinline__ double exp_fast(double a)
+{
+    a = sel_min(sel_max(a, -708.0), 709.0);
+    const double MAGIC = 6755399441055744.0;             // 1.5 * 2^52: round-to-nearest-integer by addition
+    double t = fma(a, 1.4426950408889634074, MAGIC);
+    int k = __double2loint(t);
+    double kd = t - MAGIC;
+    double r = fma(kd, -6.93147180559945286227e-01, a);
+    r = fma(kd, -2.31904681384629955842e-17, r);
+    double p = 1.6059043836821613e-10;                   // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);                 // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);                // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);                // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);               // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);                 // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);                // 1/7!
+    p = fma(p, r, 1.3888888888888889e-03);               // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);                // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);               // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);               // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// log(x) for normal x > 0 (callers clamp to >= 1e-300): x = 2^e m with m in [sqrt(1/2), sqrt 2), s = (m-1)/(m+1),
+// log m = 2 atanh s = 2s (1 + z/3 + z^2/5 + ... + z^10/21), z = s^2 <= 0.0295 (truncation 6e-19).  ~35 instructions
+// against 104 (log) / 256 (log1p) for the library versions; <= 2 ulp (tests/test_gpu_sfcc.py).
+__device__ __forceinline__ double log_pos(double x)
+{
+    int hi = __double2hiint(x), lo = __double2loint(x);
+    int e = (hi >> 20) - 1023;
+    int mh = (hi & 0x000fffff) | 0x3ff00000;
+    bool big = mh > 0x3ff6a09e;                          // m > sqrt 2
+    mh = big ? mh - 0x00100000 : mh;
+    e = big ? e + 1 : e;
+    double m = __hiloint2double(mh, lo);
+    double f = m - 1.0;                                  // exact
+    double s = f * rcp_fast(m + 1.0);
+    double z = s * s;
+    double p = 1.0 / 21.0;
+    p = fma(p, z, 1.0 / 19.0);
+    p = fma(p, z, 1.0 / 17.0);
+    p = fma(p, z, 1.0 / 15.0);
+    p = fma(p, z, 1.0 / 13.0);
+    p = fma(p, z, 1.0 / 11.0);
+    p = fma(p, z, 1.0 / 9.0);
+    p = fma(p, z, 1.0 / 7.0);
+    p = fma(p, z, 1.0 / 5.0);
+    p = fma(p, z, 1.0 / 3.0);
+    double s2 = s + s;
+    double lm = fma(s2 * z, p, s2);
+    double ed = (double)e;
+    return fma(ed, 6.93147180559945286227e-01, fma(ed, 2.31904681384629955842e-17, lm));
+}
+
+
 __device__ __forceinline__ double warp_max(double v)
 {
 #pragma unroll
@@ -192,26 +254,19 @@ __device__ __forceinline__ double lerp_table(const double* __restrict__ xk, cons
     return (1.0 - w) * __ldg(yk + lo) + w * __ldg(yk + lo + 1);
 }
 
-__device__ __forceinline__ double lut_eval(const double* __restrict__ Hk, const double* __restrict__ Tk, int nk, int extrap, double H)
-{
-    if (extrap == 0) {
-        if (H <= __ldg(Hk)) return __ldg(Tk);
-        if (H >= __ldg(Hk + nk - 1)) return __ldg(Tk + nk - 1);
-    }
-    return lerp_table(Hk, Tk, nk, H);
-}
-
-// Presolver interpolant through the bucket index: one bucket load narrows the segment to <= ~16 candidates, then a
-// fixed-trip, branch-free bisection (no warp divergence), then T = T_i + (H - H_i) * slope_i.  Linear extrapolation
-// uses the end segments; flat extrapolation clamps H to the knot range first.
+// Presolver interpolant through the bucket index.  The host sizes the uniform H-grid so that almost every bucket holds
+// at most one knot: one bucket load gives the first candidate segment lo and the number of bisection trips over
+// [lo, lo + 2^trips - 1] (0 or 1 almost everywhere), then T = T_i + (H - H_i) * slope_i.  Linear extrapolation uses the
+// end segments; flat extrapolation clamps H to the knot range first.
 __device__ __forceinline__ double lut_eval_bucket(const double* __restrict__ Hk, const double* __restrict__ Tk, const double* __restrict__ Sk,
-                                                  const int2* __restrict__ B, double hmin, double hmax, double invbw, int extrap, int nit, double H)
+                                                  const unsigned* __restrict__ B, double hmin, double hmax, double invbw, double nbm1,
+                                                  int extrap, double H)
 {
     if (extrap == 0) H = sel_min(sel_max(H, hmin), hmax);
-    double fb = sel_min(sel_max((H - hmin) * invbw, 0.0), (double)(LUT_NB - 1));
-    int2 r = __ldg(B + (int)fb);
-    int lo = r.x, hi = r.y;
-    for (int k = 0; k < nit; ++k) {
+    double fb = sel_min(sel_max((H - hmin) * invbw, 0.0), nbm1);
+    unsigned w = __ldg(B + (int)fb);
+    int lo = (int)(w & 0xffffffu), hi = lo + (1 << (w >> 24)) - 1;
+    for (int k = (int)(w >> 24); k > 0; --k) {
         int mid = (lo + hi + 1) >> 1;
         bool p = __ldg(Hk + mid) <= H;
         lo = p ? mid : lo;
@@ -220,38 +275,19 @@ __device__ __forceinline__ double lut_eval_bucket(const double* __restrict__ Hk,
     return fma(H - __ldg(Hk + lo), __ldg(Sk + lo), __ldg(Tk + lo));
 }
 
-// LUT evaluation with a cached knot interval (H moves slowly between steps): probe the cached interval first, fall back
-// to the binary search.  Same result as lut_eval.
-__device__ __forceinline__ double lut_eval_cached(const double* __restrict__ Hk, const double* __restrict__ Tk, int nk, int extrap, double H, int& idx)
-{
-    int i = min(max(idx, 0), nk - 2);
-    double x0 = __ldg(Hk + i), x1 = __ldg(Hk + i + 1);
-    bool inside = (x0 <= H) && (H < x1);
-    bool edge_lo = (i == 0) && (H < x0), edge_hi = (i == nk - 2) && (H >= x1);
-    if (!(inside || edge_lo || edge_hi)) {
-        int lo = 0, hi = nk - 1;
-        while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (__ldg(Hk + mid) <= H) lo = mid; else hi = mid;
-        }
-        i = lo; x0 = __ldg(Hk + i); x1 = __ldg(Hk + i + 1);
-    }
-    idx = i;
-    if (extrap == 0) {
-        if (H <= __ldg(Hk)) return __ldg(Tk);
-        if (H >= __ldg(Hk + nk - 1)) return __ldg(Tk + nk - 1);
-    }
-    double w = (H - x0) / (x1 - x0);
-    return (1.0 - w) * __ldg(Tk + i) + w * __ldg(Tk + i + 1);
-}
-
-// x^n and (1+x^n)^-m for x > 0 through exp/log.  Out of line on purpose: two exp + two log are ~200 instructions, and the
+// x^n and (1+x^n)^-m for x > 0 through exp/log.  Out of line on purpose: two exp + two log are >100 instructions, and the
 // callers are unrolled over the cells of a lane (and sit inside the Newton loop) -- inlined, the step loop overflows the
 // instruction cache (ncu: `no_instruction` was the second largest stall).
-static __device__ __noinline__ void vg_powers(double x, double n, double m, double& xn, double& pb)
+__device__ __forceinline__ void vg_powers_body(double x, double n, double m, double& xn, double& pb)
 {
-    xn = exp(n * log(x));
-    pb = exp(-m * log1p(xn));
+    xn = exp_fast(n * log_pos(x));
+    pb = exp_fast(-m * log_pos(1.0 + xn));       // 1 + x^n rounds with absolute error 1.1e-16: relative 1e-16 m in pb
+}
+static __device__ __noinline__ double2 vg_powers(double x, double n, double m)
+{
+    double2 r;
+    vg_powers_body(x, n, m, r.x, r.y);
+    return r;
 }
 
 // van Genuchten θ(ψ) and dθ/dψ for ψ <= 0; θsat for ψ > 0.  x^n and (1+x^n)^-m go through exp/log (x > 0, base >= 1:
@@ -268,8 +304,8 @@ __device__ __forceinline__ double vg_theta(double psi, double thsat, double thre
             return fma(d, rs, thres);
         }
         if (x > 0.0) {
-            double xn, pb;
-            vg_powers(x, n, m, xn, pb);
+            double2 r = vg_powers(x, n, m);
+            double xn = r.x, pb = r.y;
             double base = 1.0 + xn;
             dth = d * m * n * alpha * (xn * rcp_fast(x)) * (pb * rcp_fast(base));
             return fma(d, pb, thres);

@@ -61,10 +61,10 @@ __device__ __forceinline__ void layer_consts(const Dev& P, long long col, int l,
             int id = P.table_map ? P.table_map[ix] : l;
             int off = P.lut_off[id], nk = P.lut_len[id];
             to[0] = off; to[1] = nk;
-            tl[0] = P.lut_extrap[id]; tl[1] = P.lut_nit[id];
+            tl[0] = P.lut_extrap[id]; tl[1] = 0;
             reinterpret_cast<int*>(c + LC_BOFF)[0] = P.lut_boff[id];
-            double hmin = P.lutH[off], hmax = P.lutH[off + nk - 1];
-            c[LC_HMIN] = hmin; c[LC_HMAX] = hmax; c[LC_INVBW] = (double)LUT_NB / (hmax - hmin);
+            double hmin = P.lutH[off], hmax = P.lutH[off + nk - 1], nb = (double)P.lut_nb[id];
+            c[LC_HMIN] = hmin; c[LC_HMAX] = hmax; c[LC_INVBW] = nb / (hmax - hmin); c[LC_NBM1] = nb - 1.0;
         }
     }
 }
@@ -72,6 +72,14 @@ __device__ __forceinline__ void layer_consts(const Dev& P, long long col, int l,
 __device__ __forceinline__ void stage_layer_consts(const Dev& P, long long col, double* lc, int lane)
 {
     for (int l = lane; l < P.n_layers; l += 32) layer_consts(P, col, l, lc + l * LC_STRIDE);
+}
+
+// true when every layer of the staged column has van Genuchten n == 2 (the rsqrt shortcut of stage_a_lut applies)
+__device__ __forceinline__ bool all_layers_n2(const Dev& P, const double* lcw, int lane)
+{
+    bool ok = true;
+    for (int l = lane; l < P.n_layers; l += 32) ok = ok && (lcw[l * LC_STRIDE + LC_N] == 2.0);
+    return __all_sync(FULL, ok);
 }
 
 // Safeguarded Newton for T*C(θw(T)) + Lθw(T) = H (monotone in T; same bracketing as the oracle).
@@ -91,10 +99,15 @@ __device__ __forceinline__ void sfcc_newton_solve(const double* lc, double L, do
         dHdT = C + dth * (L + T * dC);                 // heat_methods.jl:105
         if (r > 0.0) hi = T; else lo = T;
         double Tn = EXACT ? T - r / dHdT : fma(-r, rcp_fast(dHdT), T);
-        bool safe = (Tn >= lo && Tn <= hi);            // inclusive: a converged step may land on the bracket end (NaN -> false)
+        // a Newton step is taken if it falls strictly inside the bracket, or ON its end when it is a converged step (the
+        // strict test alone would bisect there; the inclusive test alone lets Newton 2-cycle between the bracket ends:
+        // unfrozen side -> far frozen side -> back).  NaN -> bisect.
+        const double tol = (EXACT ? 1e-15 : 1e-9) * fmax(1.0, fabs(Tn));
+        bool small = fabs(Tn - T) <= tol;
+        bool safe = (Tn > lo && Tn < hi) || (small && Tn >= lo && Tn <= hi);
         if (!safe) Tn = 0.5 * (lo + hi);
         double dT = Tn - T;
-        bool done = safe && fabs(dT) <= (EXACT ? 1e-15 : 1e-9) * fmax(1.0, fabs(Tn));
+        bool done = fabs(dT) <= tol;                   // a bisection step this small means the bracket has collapsed
         T = Tn;
         if (done) {
             if (EXACT) {
@@ -115,7 +128,7 @@ __device__ __forceinline__ double lut_T(const Dev& P, const double* lc, double H
     const int* to = reinterpret_cast<const int*>(lc + LC_TABOFF);
     const int* tl = reinterpret_cast<const int*>(lc + LC_TABLEN);
     int off = to[0], boff = reinterpret_cast<const int*>(lc + LC_BOFF)[0];
-    return lut_eval_bucket(P.lutH + off, P.lutT + off, P.lutS + off, P.lutB + boff, lc[LC_HMIN], lc[LC_HMAX], lc[LC_INVBW], tl[0], tl[1], H);
+    return lut_eval_bucket(P.lutH + off, P.lutT + off, P.lutS + off, P.lutB + boff, lc[LC_HMIN], lc[LC_HMAX], lc[LC_INVBW], lc[LC_NBM1], tl[0], H);
 }
 
 // H -> (T, θw, C, dHdT, dθw/dT, kc) for one cell.
@@ -168,6 +181,93 @@ __device__ __forceinline__ void freezethaw_cell(const Dev& P, const double* lc, 
     else freezethaw_body<MODE, EXACT>(P, lc, H, dC, dK, T, thw, C, dHdT, dth, kc);
 }
 
+// Stage A for stratigraphies whose layers ALL use an SFCC with the presolver LUT (MODE 1), written phase by phase over
+// the CPL cells of a lane so that the independent chains overlap: (1) bucket loads, (2) ONE fixed-trip bisection loop
+// that advances all cells together (the per-cell formulation ran CPL dependent load chains one after the other),
+// (3) T from the segment, (4) matric potential, (5) the van Genuchten powers of all cells in one block (exp/log chains
+// of different cells interleave; warp-uniform rsqrt shortcut when every n == 2), (6) C, dH/dT, kc.
+// Same arithmetic as freezethaw_body<1, .>.
+// DERIV = false skips dθw/dT, C and dH/dT (only the CFL limiter and the diagnostics kernel need them).
+template <int CPL, bool DERIV = true>
+__device__ __forceinline__ void stage_a_lut(const Dev& P, const double* lcw, const int (&loff)[CPL], const double (&H)[CPL],
+                                            double (&T)[CPL], double (&thw)[CPL], double (&C)[CPL], double (&dHdT)[CPL],
+                                            double (&dth)[CPL], double (&kc)[CPL], double dC, double dK, bool n2)
+{
+    int lo[CPL], hi[CPL];
+    double Hq[CPL];
+    unsigned trips = 0;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+        const double* lc = lcw + loff[j];
+        double hmin = lc[LC_HMIN], hmax = lc[LC_HMAX];
+        Hq[j] = (reinterpret_cast<const int*>(lc + LC_TABLEN)[0] == 0) ? sel_min(sel_max(H[j], hmin), hmax) : H[j];
+        double fb = sel_min(sel_max((Hq[j] - hmin) * lc[LC_INVBW], 0.0), lc[LC_NBM1]);
+        unsigned w = __ldg(P.lutB + reinterpret_cast<const int*>(lc + LC_BOFF)[0] + (int)fb);
+        lo[j] = reinterpret_cast<const int*>(lc + LC_TABOFF)[0] + (int)(w & 0xffffffu);
+        hi[j] = lo[j] + (1 << (w >> 24)) - 1;
+        trips = max(trips, w >> 24);
+    }
+    // trip count of the bisection = the widest candidate range any cell of the warp drew (0 or 1 almost everywhere; the
+    // knots of a presolver table pile up only at the kink of the freeze curve)
+    const int nit = (int)__reduce_max_sync(FULL, trips);
+    for (int k = 0; k < nit; ++k) {
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            int mid = (lo[j] + hi[j] + 1) >> 1;
+            bool p = __ldg(P.lutH + mid) <= Hq[j];
+            lo[j] = p ? mid : lo[j];
+            hi[j] = p ? hi[j] : mid - 1;
+        }
+    }
+    double x[CPL], dpsi[CPL], pb[CPL], q[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+        const double* lc = lcw + loff[j];
+        const int i = lo[j];
+        T[j] = fma(Hq[j] - __ldg(P.lutH + i), __ldg(P.lutS + i), __ldg(P.lutT + i));
+        double TK = T[j] + 273.15, Tstar = lc[LC_TSTAR];
+        bool frozen = (Tstar - TK) >= 0.0;
+        double psi = frozen ? fma(lc[LC_CFAC], TK - Tstar, lc[LC_PSI0]) : lc[LC_PSI0];
+        if (DERIV) dpsi[j] = frozen ? lc[LC_CFAC] : 0.0;
+        x[j] = (psi <= 0.0) ? fabs(-lc[LC_ALPHA] * psi) : -1.0;      // -1 marks ψ > 0 (θw = θsat)
+    }
+    if (n2) {
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            double rs = rsqrt_fast(fma(x[j], x[j], 1.0));
+            pb[j] = rs;
+            if (DERIV) q[j] = (lcw + loff[j])[LC_ALPHA] * x[j] * (rs * rs * rs);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            const double* lc = lcw + loff[j];
+            double n = lc[LC_N], m = lc[LC_M];
+            pb[j] = 1.0; q[j] = 0.0;
+            if (x[j] > 0.0) {                         // skipped by the whole warp for thawed, saturated cells
+                double2 r = vg_powers(x[j], n, m);
+                pb[j] = r.y;
+                if (DERIV) q[j] = m * n * lc[LC_ALPHA] * (r.x * rcp_fast(x[j])) * (r.y * rcp_fast(1.0 + r.x));
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+        const double* lc = lcw + loff[j];
+        double thsat = sel_max(lc[LC_THWI], lc[LC_POR]);
+        double d = thsat - lc[LC_THRES];
+        bool sat = x[j] < 0.0;
+        thw[j] = sat ? thsat : fma(d, pb[j], lc[LC_THRES]);
+        if (DERIV) {
+            dth[j] = sat ? 0.0 : (d * q[j]) * dpsi[j];
+            C[j] = fma(dC, thw[j], lc[LC_CBS]);
+            dHdT[j] = C[j] + dth[j] * (P.L + T[j] * dC);     // heat_methods.jl:105
+        }
+        double sk = fma(dK, thw[j], lc[LC_KB]);
+        kc[j] = sk * sk;
+    }
+}
+
 // Warp-uniform forcing evaluation with a cursor into the table (t only moves forward).
 struct ForcingCursor {
     int idx;
@@ -189,7 +289,8 @@ __device__ __forceinline__ void forcing_seek(const Forcing& F, ForcingCursor& c,
 __device__ __forceinline__ double forcing_eval(const Forcing& F, ForcingCursor& c, double t, int& status)
 {
     if (F.kind == 0) return F.value;
-    if (F.kind == 1) return F.amplitude * sin(2.0 * M_PI * (t / F.period) + F.phase) + F.level;  // simple_bc.jl:37
+    // simple_bc.jl:37  A sin(2π t/P + φ) + c, as sinpi(2 (t/P) + φ/π): exact argument reduction, a third of sin()'s instructions
+    if (F.kind == 1) return fma(F.amplitude, sinpi(fma(2.0, t / F.period, F.phase * 0.31830988618379067154)), F.level);
     if (t < __ldg(F.t) || t > __ldg(F.t + F.n - 1)) { status |= 4; return nan(""); }              // providers.jl:30-33
     while (t >= c.tb && c.idx < F.n - 2) {
         ++c.idx;
@@ -202,8 +303,13 @@ __device__ __forceinline__ double forcing_eval(const Forcing& F, ForcingCursor& 
 }
 
 // -------------------------------------------------------------------------------------------------
+#ifdef CGB_EULER_MINB
+#define CGB_EULER_BOUNDS __launch_bounds__(128, CGB_EULER_MINB)
+#else
+#define CGB_EULER_BOUNDS __launch_bounds__(128)
+#endif
 template <int CPL, int MODE, bool DIAG>
-__global__ void __launch_bounds__(128) k_heat_euler(const __grid_constant__ Dev P, double t_target, Diag D)
+__global__ void CGB_EULER_BOUNDS k_heat_euler(const __grid_constant__ Dev P, double t_target, Diag D)
 {
     extern __shared__ double smem[];
     double* sInvDk = smem;
@@ -252,6 +358,7 @@ __global__ void __launch_bounds__(128) k_heat_euler(const __grid_constant__ Dev 
         __syncwarp();
         stage_layer_consts(P, col, lcw, lane);
         __syncwarp();
+        const bool n2 = (MODE == 1) && all_layers_n2(P, lcw, lane);
 
         double H[CPL], T[CPL];
 #pragma unroll
@@ -277,9 +384,13 @@ __global__ void __launch_bounds__(128) k_heat_euler(const __grid_constant__ Dev 
 
             // ---- stage A: H -> T, θw, C, kc
             double kc[CPL], thw[CPL], C[CPL], dHdT[CPL], dth[CPL];
+            if (MODE == 1) {
+                stage_a_lut<CPL>(P, lcw, loff, H, T, thw, C, dHdT, dth, kc, dC, dK, n2);
+            } else {
 #pragma unroll
-            for (int j = 0; j < CPL; ++j)
-                freezethaw_cell<MODE, DIAG>(P, lcw + loff[j], H[j], dC, dK, T[j], thw[j], C[j], dHdT[j], dth[j], kc[j]);
+                for (int j = 0; j < CPL; ++j)
+                    freezethaw_cell<MODE, DIAG>(P, lcw + loff[j], H[j], dC, dK, T[j], thw[j], C[j], dHdT[j], dth[j], kc[j]);
+            }
 
             if (!DIAG && (D.T || D.thw) && !(t + dt < t_target)) {
                 // last step of the interval: the reference saves the diagnostics cached by this RHS evaluation (state BEFORE
@@ -329,7 +440,8 @@ __global__ void __launch_bounds__(128) k_heat_euler(const __grid_constant__ Dev 
                 }
                 int s = j * 32 + lane;
                 dH[j] = (je[j] - jlow) * sInvDk[s];
-                maxabs = fmax(maxabs, fabs(dH[j]));
+                double a = fabs(dH[j]);
+                maxabs = (a > maxabs) ? a : maxabs;                       // fmax() is ~7 instructions on sm_100; NaN is skipped as by fmax
                 if (P.limiter == 1) {
                     double dx = sDk[s];
                     double v = dHdT[j] * rcp_fast(kc[j]);
@@ -381,9 +493,9 @@ __global__ void __launch_bounds__(128) k_heat_euler(const __grid_constant__ Dev 
                 if (!(lim > 0.0)) lim = INFINITY;                        // heat_conduction.jl:189
             }
             if (!(lim > 0.0)) status |= 8;                                // tile.jl:174
-            double dtn = fmax(fmin(lim, P.dtmax), P.dtmin);
-            if (t < t_target) dtn = fmin(dtn, t_target - t);             // integrator.jl:126-131
-            dt = fmin(P.dtmax, dtn);                                      // integrator.jl:89
+            double dtn = sel_max(sel_min(lim, P.dtmax), P.dtmin);
+            if (t < t_target) dtn = sel_min(dtn, t_target - t);          // integrator.jl:126-131
+            dt = sel_min(dtn, P.dtmax);                                   // integrator.jl:89
             if (status & 4) break;
         }
         if (!DIAG) {

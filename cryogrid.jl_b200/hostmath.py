@@ -138,9 +138,11 @@ def sfcc_newton(fc, tp, por, sat, org, H, T0):
         else:
             lo = T
         Tn = T - r / dHdT
-        if not (lo <= Tn <= hi):
+        small = abs(Tn - T) <= 1e-15 * max(1.0, abs(Tn))
+        safe = (lo < Tn < hi) or (small and lo <= Tn <= hi)     # see sfcc_newton_solve in csrc/cgb_euler.cuh
+        if not safe:
             Tn = 0.5 * (lo + hi)
-        done = abs(Tn - T) <= 1e-15 * max(1.0, abs(Tn))
+        done = abs(Tn - T) <= 1e-15 * max(1.0, abs(Tn))         # converged, or the bracket has collapsed
         T = Tn
         if done:
             break

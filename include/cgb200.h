@@ -219,6 +219,9 @@ int cgb_profile_read(cgb_handle* h, int64_t* n_launches, double* total_ms);
 /* Self-test: evaluates on the device the reciprocal sequences the kernels use in place of IEEE division
  * (raw MUFU.RCP64H seed, seed + 2 Newton steps, seed + 1 cubic step) for n host inputs. */
 int cgb_selftest_rcp(const double* x, int64_t n, double* out_raw, double* out_newton2, double* out_cubic);
+/* Self-test: the kernels' exp / log replacements (van Genuchten powers, FreezeCurves.jl closed forms):
+ * out_exp[i] = exp_fast(x[i]) (argument clamped to [-708, 709]), out_log[i] = log_pos(|x[i]|) (normal range). */
+int cgb_selftest_explog(const double* x, int64_t n, double* out_exp, double* out_log);
 
 #ifdef __cplusplus
 }

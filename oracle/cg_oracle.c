@@ -253,8 +253,12 @@ double cg_sfcc_newton(const cg_freezecurve* fc, const cg_thermal* tp, double por
         double r = sfcc_enthalpy(fc, tp, por, sat, org, T, &dHdT, NULL) - H;
         if (r > 0.0) hi = T; else lo = T;
         double Tn = T - r / dHdT;
-        if (!(Tn >= lo && Tn <= hi)) Tn = 0.5 * (lo + hi); /* inclusive: a converged step may land on the bracket end */
-        if (fabs(Tn - T) <= 1e-15 * fmax(1.0, fabs(Tn))) { T = Tn; break; }
+        /* Newton step if strictly inside the bracket, or on its end when converged (strict-only bisects
+         * there; inclusive-only lets Newton 2-cycle between the bracket ends) */
+        int small = fabs(Tn - T) <= 1e-15 * fmax(1.0, fabs(Tn));
+        int safe = (Tn > lo && Tn < hi) || (small && Tn >= lo && Tn <= hi);
+        if (!safe) Tn = 0.5 * (lo + hi);
+        if (fabs(Tn - T) <= 1e-15 * fmax(1.0, fabs(Tn))) { T = Tn; break; } /* converged, or bracket collapsed */
         T = Tn;
     }
     return T;

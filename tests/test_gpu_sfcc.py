@@ -111,3 +111,38 @@ def test_caller_supplied_table_is_used(orc):
     np.testing.assert_allclose(T, np.interp(H, Hk, Tk), rtol=1e-13, atol=1e-13)
     _check_rhs(orc, tile, eng, H, 0.0)
     eng.close()
+
+
+def test_exp_log_replacements_accuracy():
+    # the van Genuchten powers use exp_fast / log_pos (cgb_common.cuh) instead of the CUDA library's exp / log / log1p;
+    # check them against libm over the operand ranges that occur (x = α|ψ| from 1e-300 to 1e12, exponents to ±700)
+    from cryogrid_jl_b200 import _lib as L
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.uniform(-700.0, 700.0, 40000), rng.uniform(-2.0, 2.0, 20000), 10.0 ** rng.uniform(-300, 300, 20000),
+                        1.0 + rng.uniform(-1e-3, 1e-3, 20000), 1.0 + 10.0 ** rng.uniform(-16, 0, 20000)])
+    ex, lg = np.empty_like(x), np.empty_like(x)
+    assert L.load().cgb_selftest_explog(L.dptr(x), x.size, L.dptr(ex), L.dptr(lg)) == 0
+    a = np.clip(x, -708.0, 709.0)
+    e_exp = np.max(np.abs(ex - np.exp(a)) / np.exp(a))
+    ref = np.log(np.abs(x))
+    # log: relative error where |log| is not tiny, absolute error (in ulps of 1) near x = 1
+    e_log = np.max(np.abs(lg - ref) / np.maximum(np.abs(ref), 1e-3))
+    near1 = np.abs(ref) < 1e-3
+    e_log1 = np.max(np.abs(lg[near1] - ref[near1]) / np.maximum(np.abs(ref[near1]), 1e-17))
+    print(f"exp_fast rel. error {e_exp:.3e}, log_pos rel. error {e_log:.3e}, near 1: {e_log1:.3e}")
+    assert e_exp < 4.5e-16
+    assert e_log < 4.5e-16
+    assert e_log1 < 6e-16
+    # clamping: arguments beyond the range stay finite and monotone
+    assert np.all(np.isfinite(ex)) and np.all(ex > 0.0)
+
+
+@pytest.mark.parametrize("solver", ["lut", "newton"])
+def test_advance_sfcc_cfl_limiter(orc, solver):
+    # CFL limiter on SFCC columns: the stepping kernel evaluates dH/dT only in this configuration (LUT mode)
+    tile = _samoylov_sfcc_tile(3, solver, seed=5)
+    tile.heat.dtlim = cg.CFL(0.5, cg.MaxDelta(5e4))
+    H0 = cg.initialcondition(tile)
+    eng = cg.Engine(tile, dtmax=900.0)
+    _check_advance(orc, tile, eng, H0, 0.0, [86400.0, 5 * 86400.0], dtmax=900.0)
+    eng.close()
