@@ -370,6 +370,7 @@ static int finalize(cgb_handle* h)
             double *pt, *py;
             rc |= dev_upload(h, &pt, f.t); rc |= dev_upload(h, &py, f.y);
             F.t = pt; F.y = py;
+            F.inv_step = (double)(f.t.size() - 1) / (f.t.back() - f.t.front());
             if (w == 0) {
                 std::vector<double> inv(f.t.size() - 1);
                 for (size_t k = 0; k + 1 < f.t.size(); ++k) inv[k] = 1.0 / (f.t[k + 1] - f.t[k]);
@@ -585,31 +586,52 @@ static bool fast_path(const cgb_handle* h)
            h->cfg.limiter == CGB_LIMITER_MAXDELTA && h->fast_ok;
 }
 
-static int launch_advance_inner(cgb_handle* h, double t_target, double* saveT, double* saveW)
+static bool lite_thread_variant()
 {
-    Diag D{};
-    D.T = saveT; D.thw = saveW;
-    if (h->cfg.physics == CGB_PHYSICS_HEAT_SALT) return cgb_salt_launch(h, t_target, false, D, nullptr);
-    if (h->cfg.stepper == CGB_STEPPER_LITE_IMPLICIT) {
-        // "Thomas per thread or partition/PCR per warp": the warp variant is the default; CGB_LITE_VARIANT=thread selects
-        // the reference-order Thomas sweep (re-read on every launch so that tests can switch in-process)
-        const char* v = getenv("CGB_LITE_VARIANT");
-        if (v && std::strcmp(v, "thread") == 0) return cgb_launch_lite_thread(h, t_target, false, D);
-        return cgb_launch_lite_warp(h, t_target, saveT, saveW);
-    }
-    bool fast = all_freewater(h) && h->cfg.limiter == CGB_LIMITER_MAXDELTA && h->fast_ok;
-    if (fast) return cgb_launch_fast(h, t_target, saveT, saveW);
-    // solver mode of the general kernel: 1 = every layer SFCC + LUT, 2 = every layer SFCC + Newton, 3 = every layer FreeWater, 0 = mixed
+    // "Thomas per thread or partition/PCR per warp": the warp variant is the default; CGB_LITE_VARIANT=thread selects
+    // the reference-order Thomas sweep (re-read on every launch so that tests can switch in-process)
+    const char* v = getenv("CGB_LITE_VARIANT");
+    return v && std::strcmp(v, "thread") == 0;
+}
+
+// solver mode of the general explicit kernel: 1 = every layer SFCC + LUT, 2 = every layer SFCC + Newton,
+// 3 = every layer FreeWater, 0 = mixed
+static int euler_mode(const cgb_handle* h)
+{
     bool all_lut = true, all_newton = true;
     for (int l = 0; l < h->nl; ++l) {
         bool sf = h->fc_kind[l] != CGB_FC_FREEWATER;
         all_lut &= sf && h->fc_solver[l] == CGB_SOLVER_LUT;
         all_newton &= sf && h->fc_solver[l] == CGB_SOLVER_NEWTON;
     }
-    if (all_lut) return cgb_launch_euler(h, 1, false, t_target, D);
-    if (all_newton) return cgb_launch_euler(h, 2, false, t_target, D);
-    if (all_freewater(h)) return cgb_launch_euler(h, 3, false, t_target, D);
-    return cgb_launch_euler(h, 0, false, t_target, D);
+    return all_lut ? 1 : all_newton ? 2 : all_freewater(h) ? 3 : 0;
+}
+
+// the stepping kernels that carry a column through several save times per launch (device-side saveat)
+static bool multi_target_path(const cgb_handle* h)
+{
+    if (h->cfg.physics != CGB_PHYSICS_HEAT) return false;
+    if (h->cfg.stepper == CGB_STEPPER_LITE_IMPLICIT) return !lite_thread_variant();
+    return true;
+}
+
+// n save times in one launch; the diagnostics saved at targets[k] go to saveT/saveW + k*save_stride
+static int launch_multi(cgb_handle* h, const double* targets, int n, double* saveT, double* saveW, long long save_stride)
+{
+    if (h->cfg.stepper == CGB_STEPPER_LITE_IMPLICIT) return cgb_launch_lite_warp_multi(h, targets, n, saveT, saveW, save_stride);
+    if (fast_path(h)) return cgb_launch_fast_multi(h, targets, n, saveT, saveW, save_stride);
+    Diag D{};
+    D.T = saveT; D.thw = saveW;
+    return cgb_launch_euler_step_multi(h, euler_mode(h), targets, n, D, save_stride);
+}
+
+static int launch_advance_inner(cgb_handle* h, double t_target, double* saveT, double* saveW)
+{
+    Diag D{};
+    D.T = saveT; D.thw = saveW;
+    if (h->cfg.physics == CGB_PHYSICS_HEAT_SALT) return cgb_salt_launch(h, t_target, false, D, nullptr);
+    if (h->cfg.stepper == CGB_STEPPER_LITE_IMPLICIT && lite_thread_variant()) return cgb_launch_lite_thread(h, t_target, false, D);
+    return launch_multi(h, &t_target, 1, saveT, saveW, 0);
 }
 
 static int launch_diag(cgb_handle* h, double t, const Diag& D)
@@ -746,9 +768,9 @@ extern "C" int cgb_solve_saveat(cgb_handle* h, const double* tsave, int64_t nsav
         }
         h->stage_elems = per_save;
     }
-    // Device-side saveat for the FreeWater fast path: up to `chunk` save times per launch -- a column is carried through all
-    // of them in registers, the saved fields of the chunk land contiguously in one staging buffer and leave in one copy.
-    bool chunked = fast_path(h) && !sv.Tnow && !sv.Wnow;
+    // Device-side saveat: up to `chunk` save times per launch -- a column is carried through all of them in registers, the
+    // saved fields of the chunk land contiguously in one staging buffer and leave in one copy.
+    bool chunked = multi_target_path(h) && !sv.Tnow && !sv.Wnow;
     for (auto& n : sv.names) chunked = chunked && n != "H";   // H is the live state: it must be copied out after every save
     for (int64_t s = 1; chunked && s < nsave; ++s) chunked = tsave[s] > tsave[s - 1];
     if (chunked && nsave >= 2 && tsave[0] > h->t_front) {
@@ -773,7 +795,7 @@ extern "C" int cgb_solve_saveat(cgb_handle* h, const double* tsave, int64_t nsav
             }
             cudaEvent_t pa = nullptr, pb = nullptr;
             if (h->profiling) { cudaEventCreate(&pa); cudaEventCreate(&pb); cudaEventRecord(pa, h->stream); }
-            rc = cgb_launch_fast_multi(h, tsave + s0, n, bT, bW, (long long)per_save);
+            rc = launch_multi(h, tsave + s0, n, bT, bW, (long long)per_save);
             if (h->profiling) { cudaEventRecord(pb, h->stream); h->prof_events.emplace_back(pa, pb); }
             if (rc) return rc;
             h->t_front = tsave[s0 + n - 1];

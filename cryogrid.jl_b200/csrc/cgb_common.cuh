@@ -45,6 +45,16 @@ struct Forcing {
     double period, amplitude, phase, level;
     const double* t;
     const double* y;
+    double inv_step;          // (n-1)/(t[n-1]-t[0]): first guess of a knot index (exact for evenly spaced tables)
+};
+
+// Save times of one launch, passed by value: a column is advanced through all of them without leaving its warp, and the
+// diagnostics to be saved at target k go to saveT/saveW + k*save_stride (device-side saveat).
+constexpr int FAST_MAX_TARGETS = 16;
+struct FastTargets {
+    double t[FAST_MAX_TARGETS];
+    int n;
+    long long save_stride;   // elements between consecutive saves in saveT / saveW
 };
 
 // Everything a kernel needs; passed by value (__grid_constant__).

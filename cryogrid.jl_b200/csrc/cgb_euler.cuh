@@ -276,10 +276,16 @@ struct ForcingCursor {
 
 __device__ __forceinline__ void forcing_seek(const Forcing& F, ForcingCursor& c, double t)
 {
-    int lo = 0, hi = F.n - 1;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (__ldg(F.t + mid) <= t) lo = mid; else hi = mid;
+    // guess from the mean knot spacing (exact for the evenly spaced forcing tables of the reference's loaders), verified;
+    // a bisection -- ~log2(n) dependent global loads per column and launch -- only when the guess misses
+    int lo = min(max((int)((t - __ldg(F.t)) * F.inv_step), 0), F.n - 2);
+    if (!(__ldg(F.t + lo) <= t && t <= __ldg(F.t + lo + 1))) {
+        lo = 0;
+        int hi = F.n - 1;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (__ldg(F.t + mid) <= t) lo = mid; else hi = mid;
+        }
     }
     c.idx = lo;
     c.ta = __ldg(F.t + lo); c.tb = __ldg(F.t + lo + 1);

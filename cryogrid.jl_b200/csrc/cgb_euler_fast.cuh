@@ -31,15 +31,6 @@ __device__ __forceinline__ double warp_max_nonneg(double v)
 template <bool CUBIC>
 __device__ __forceinline__ double rcp_sel(double a) { return CUBIC ? rcp_fast3(a) : rcp_fast(a); }
 
-// Save times of one launch, passed by value: a column is advanced through all of them without leaving its warp, and the
-// diagnostics to be saved at target k go to saveT/saveW + k*save_stride (device-side saveat).
-constexpr int FAST_MAX_TARGETS = 16;
-struct FastTargets {
-    double t[FAST_MAX_TARGETS];
-    int n;
-    long long save_stride;   // elements between consecutive saves in saveT / saveW
-};
-
 template <int CPL, int MINB, bool CUBIC, bool SAVE>
 __global__ void __launch_bounds__(128, MINB) k_heat_euler_fast(const __grid_constant__ Dev P, const __grid_constant__ FastTargets TG,
                                                                 double* __restrict__ saveT, double* __restrict__ saveW)

@@ -50,7 +50,7 @@ struct StageA {
 #endif
 
 template <int CPL, int MODE>
-__global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, double t_target, Diag D)
+__global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, const __grid_constant__ FastTargets TG, Diag D)
 {
     extern __shared__ double smem[];
     double* sInvDk = smem;
@@ -126,6 +126,9 @@ __global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, doubl
             if (P.top_kind == 0 && P.use_nfactor) vtop = ((vtop <= 0.0) ? nf : nt) * vtop;   // heat_bc.jl:78-86
             vbot = P.bot_value ? P.bot_value[col] : forcing_eval(P.bot, cbot, tt, status);
         };
+        // device-side saveat: the column is carried through all save times of the launch in registers
+        for (int kt = 0; kt < TG.n && !(status & 4); ++kt) {
+        const double t_target = TG.t[kt];
         if (t < t_target) {
             boundary(t);
             StageA<CPL, MODE>::run(P, lcw, loff, H, T, thw, kc, dHdT, dC, dK, n2, cfl);
@@ -139,8 +142,9 @@ __global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, doubl
                 for (int j = 0; j < CPL; ++j) {
                     int i = lane * CPL + j;
                     if (i < N) {
-                        if (D.T) D.T[(size_t)i * M + col] = T[j];
-                        if (D.thw) D.thw[(size_t)i * M + col] = thw[j];
+                        size_t o = (size_t)kt * TG.save_stride + (size_t)i * M + col;
+                        if (D.T) D.T[o] = T[j];
+                        if (D.thw) D.thw[o] = thw[j];
                     }
                 }
             }
@@ -217,6 +221,7 @@ __global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, doubl
             double rem = t_target - tn;
             dt = (rem > 0.0) ? sel_min(dtn, rem) : dtn;                              // integrator.jl:126-131 (:89 is implied)
             t = tn;
+        }
         }
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {

@@ -7,9 +7,11 @@ int cgb_launch_fast_multi(cgb_handle* h, const double* targets, int n, double* s
 int cgb_fast_max_targets(void);
 int cgb_launch_euler(cgb_handle* h, int mode, bool diag, double t_target, const cgb::Diag& D);     // cgb_tu_euler.cu
 int cgb_launch_euler_step(cgb_handle* h, int mode, double t_target, const cgb::Diag& D);
+int cgb_launch_euler_step_multi(cgb_handle* h, int mode, const double* targets, int n, const cgb::Diag& D, long long save_stride);
 int cgb_launch_euler_diag(cgb_handle* h, double t, const cgb::Diag& D);                            // cgb_tu_euler_diag.cu
 int cgb_launch_lite_thread(cgb_handle* h, double t, bool diag, const cgb::Diag& D);                // cgb_tu_lite.cu
 int cgb_launch_lite_warp(cgb_handle* h, double t_target, double* saveT, double* saveW);            // cgb_tu_lite_warp.cu
+int cgb_launch_lite_warp_multi(cgb_handle* h, const double* targets, int n, double* saveT, double* saveW, long long save_stride);
 int cgb_salt_finalize(cgb_handle* h, const std::vector<double>& zc);                               // cgb_tu_salt.cu
 int cgb_salt_launch(cgb_handle* h, double t_target, bool diag, const cgb::Diag& D, void* salt_diag);
 int cgb_salt_get_diag(cgb_handle* h, const char* var, double t, double* out);

@@ -21,7 +21,8 @@
 namespace cgb {
 
 template <int CPL, int MODE, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__ Dev P, double t_target, double* __restrict__ saveT, double* __restrict__ saveW)
+__global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__ Dev P, const __grid_constant__ FastTargets TG,
+                                                         double* __restrict__ saveT, double* __restrict__ saveW)
 {
     extern __shared__ double smem[];
     double* sDk = smem;                    // [CPL*32] cell thickness (1 for padding)
@@ -82,6 +83,10 @@ __global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__
         if (P.top.kind == 2) forcing_seek(P.top, ctop, fmin(fmax(t, __ldg(P.top.t)), __ldg(P.top.t + P.top.n - 1)));
         if (P.bot.kind == 2 && !P.bot_value) forcing_seek(P.bot, cbot, fmin(fmax(t, __ldg(P.bot.t)), __ldg(P.bot.t + P.bot.n - 1)));
 
+        // device-side saveat: the column is carried through all save times of the launch in registers
+        for (int kt = 0; kt < TG.n && !(status & 6); ++kt) {
+        const double t_target = TG.t[kt];
+        bool stepped = false;
         while (t < t_target) {
             const double tn = t + dt;                                               // cglite_step.jl:9
             double vtop = forcing_eval(P.top, ctop, tn, status) + toff;
@@ -216,21 +221,29 @@ __global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__
                 if (__any_sync(FULL, bad)) { status |= 2; break; }
             }
             if (iter > P.lite_maxiters && emax > P.lite_tol) status |= 1;           // cglite_step.jl:74-77
-            t = tn; ++nsteps;
+            t = tn; ++nsteps; stepped = true;
             if (t < t_target) dt = fmin(dt, t_target - t);                          // integrator.jl:126-131
             dt = fmin(P.dtmax, dt);
             if (status & 2) break;
         }
+        if ((saveT || saveW) && stepped) {
+            // saved diagnostics = cache of the LAST tile evaluation (start of the last Picard iteration), as the
+            // reference saves them (problem.jl:67-68, Numerics/statevars.jl:81-106, cglite_step.jl:45-62)
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                int i = lane * CPL + j;
+                if (i < N) {
+                    size_t o = (size_t)kt * TG.save_stride + (size_t)i * M + col;
+                    if (saveT) saveT[o] = T[j];
+                    if (saveW) saveW[o] = W[j];
+                }
+            }
+        }
+        }
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
             int i = lane * CPL + j;
-            if (i < N) {
-                P.u[(size_t)i * M + col] = H[j];
-                // saved diagnostics = cache of the LAST tile evaluation (start of the last Picard iteration), as the
-                // reference saves them (problem.jl:67-68, Numerics/statevars.jl:81-106, cglite_step.jl:45-62)
-                if (saveT && nsteps > 0) saveT[(size_t)i * M + col] = T[j];
-                if (saveW && nsteps > 0) saveW[(size_t)i * M + col] = W[j];
-            }
+            if (i < N) P.u[(size_t)i * M + col] = H[j];
         }
         if (lane == 0) {
             P.t[col] = t; P.dt[col] = dt; P.steps[col] += nsteps; P.iters[col] += niter;
@@ -242,7 +255,7 @@ __global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__
 } // namespace cgb
 
 template <int CPL, int MODE, int MINB>
-static int lite_warp_launch_b(cgb_handle* h, double t_target, double* saveT, double* saveW)
+static int lite_warp_launch_b(cgb_handle* h, const cgb::FastTargets& tg, double* saveT, double* saveW)
 {
     using namespace cgb;
     auto kern = k_lite_warp<CPL, MODE, MINB>;
@@ -251,7 +264,7 @@ static int lite_warp_launch_b(cgb_handle* h, double t_target, double* saveT, dou
     CUDA_TRY(h, cgb_prepare_kernel(h, (const void*)kern, smem, &blocks_per_sm));
     long long grid = std::min<long long>((h->M + 3) / 4, (long long)h->num_sms * blocks_per_sm);
     CUDA_TRY(h, cudaMemsetAsync(h->dev.counter, 0, sizeof(unsigned long long), h->stream));
-    kern<<<(unsigned)grid, 128, smem, h->stream>>>(h->dev, t_target, saveT, saveW);
+    kern<<<(unsigned)grid, 128, smem, h->stream>>>(h->dev, tg, saveT, saveW);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return CGB_OK;
@@ -259,32 +272,32 @@ static int lite_warp_launch_b(cgb_handle* h, double t_target, double* saveT, dou
 
 // register budget: 2 resident CTAs (x4 warps) per SM -- MINB = 3 and 4 spill and were 8 % / 13 % slower on B200
 template <int CPL, int MODE>
-static int lite_warp_launch_m(cgb_handle* h, double t_target, double* saveT, double* saveW)
+static int lite_warp_launch_m(cgb_handle* h, const cgb::FastTargets& tg, double* saveT, double* saveW)
 {
-    return lite_warp_launch_b<CPL, MODE, 2>(h, t_target, saveT, saveW);
+    return lite_warp_launch_b<CPL, MODE, 2>(h, tg, saveT, saveW);
 }
 
 template <int CPL>
-static int lite_warp_launch_t(cgb_handle* h, double t_target, double* saveT, double* saveW)
+static int lite_warp_launch_t(cgb_handle* h, const cgb::FastTargets& tg, double* saveT, double* saveW)
 {
     bool fw = true;
     for (int l = 0; l < h->nl; ++l) fw &= h->fc_kind[l] == CGB_FC_FREEWATER;
-    return fw ? lite_warp_launch_m<CPL, 3>(h, t_target, saveT, saveW) : lite_warp_launch_m<CPL, 0>(h, t_target, saveT, saveW);
+    return fw ? lite_warp_launch_m<CPL, 3>(h, tg, saveT, saveW) : lite_warp_launch_m<CPL, 0>(h, tg, saveT, saveW);
 }
 
-static int lite_warp_launch(cgb_handle* h, double t_target, double* saveT, double* saveW)
+static int lite_warp_launch(cgb_handle* h, const cgb::FastTargets& tg, double* saveT, double* saveW)
 {
     int cpl = (h->N + 31) / 32;
     switch (cpl) {
-    case 1: return lite_warp_launch_t<1>(h, t_target, saveT, saveW);
-    case 2: return lite_warp_launch_t<2>(h, t_target, saveT, saveW);
-    case 3: case 4: return lite_warp_launch_t<4>(h, t_target, saveT, saveW);
-    case 5: case 6: return lite_warp_launch_t<6>(h, t_target, saveT, saveW);
-    case 7: return lite_warp_launch_t<7>(h, t_target, saveT, saveW);
-    case 8: return lite_warp_launch_t<8>(h, t_target, saveT, saveW);
-    case 9: return lite_warp_launch_t<9>(h, t_target, saveT, saveW);
-    case 10: return lite_warp_launch_t<10>(h, t_target, saveT, saveW);
-    case 11: case 12: return lite_warp_launch_t<12>(h, t_target, saveT, saveW);
-    default: return lite_warp_launch_t<16>(h, t_target, saveT, saveW);
+    case 1: return lite_warp_launch_t<1>(h, tg, saveT, saveW);
+    case 2: return lite_warp_launch_t<2>(h, tg, saveT, saveW);
+    case 3: case 4: return lite_warp_launch_t<4>(h, tg, saveT, saveW);
+    case 5: case 6: return lite_warp_launch_t<6>(h, tg, saveT, saveW);
+    case 7: return lite_warp_launch_t<7>(h, tg, saveT, saveW);
+    case 8: return lite_warp_launch_t<8>(h, tg, saveT, saveW);
+    case 9: return lite_warp_launch_t<9>(h, tg, saveT, saveW);
+    case 10: return lite_warp_launch_t<10>(h, tg, saveT, saveW);
+    case 11: case 12: return lite_warp_launch_t<12>(h, tg, saveT, saveW);
+    default: return lite_warp_launch_t<16>(h, tg, saveT, saveW);
     }
 }

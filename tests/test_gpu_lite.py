@@ -184,3 +184,27 @@ def test_lite_saved_diagnostics_follow_reference_cache(orc, variant):
             assert np.max(np.abs(out.T[s][:, c] - oc.work.get("T"))) <= 1e-6
             assert np.max(np.abs(out.vars["θw"][s][:, c] - oc.work.get("thw"))) <= 1e-8
             np.testing.assert_allclose(out.H[s][:, c], Hr, rtol=1e-10, atol=1e-2)
+
+
+def test_lite_multi_target_saveat_vs_oracle(orc):
+    # device-side saveat of the warp kernel (several daily saves per launch) against the oracle's work arrays, and
+    # against the one-launch-per-save path
+    tile = common.lite_ensemble_tile(ncolumns=7, seed=12)
+    H0 = cg.initialcondition(tile)
+    days = 86400.0 * np.arange(1, 20)
+    a = cg.Engine(tile, stepper="lite"); a.set_state(H0, 0.0)
+    multi = a.solve_saveat(days, ("T", "θw"))                        # chunked path
+    b = cg.Engine(tile, stepper="lite"); b.set_state(H0, 0.0)
+    single = b.solve_saveat(days, ("T", "θw", "H"))                  # H saved -> one launch per save
+    np.testing.assert_array_equal(multi[:, 0], single[:, 0])
+    np.testing.assert_array_equal(multi[:, 1], single[:, 1])
+    np.testing.assert_array_equal(a.get_state(), b.get_state())
+    assert a.stats()["kernel_launches"] < b.stats()["kernel_launches"]
+    for c in (0, 6):
+        oc = orc.OracleColumn(tile, c)
+        Hr, tr, dtr = H0[:, c].copy(), 0.0, 86400.0
+        for s, t in enumerate(days):
+            Hr, tr, dtr, *_ = oc.lite_advance(Hr, tr, dtr, t)
+            assert np.max(np.abs(multi[s, 0][:, c] - oc.work.get("T"))) <= 1e-6
+            assert np.max(np.abs(multi[s, 1][:, c] - oc.work.get("thw"))) <= 1e-8
+    a.close(); b.close()
