@@ -47,7 +47,11 @@ __global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__
         sG[s] = edge ? P.eG[i] : 0.0;
     }
     __syncthreads();
-    const double dC = P.ch_w - P.ch_i, dK = P.sk_w - P.sk_i;
+    const double dC = P.ch_w - P.ch_i, dK = P.sk_w - P.sk_i, inv_chw = 1.0 / P.ch_w;
+    // seek hints in shared memory: the cursors of the warp's previous column at its start (ta, tb, ya, yb, idx) x (top, bottom)
+    double* hint = sLCall + 4 * (P.n_layers * LC_STRIDE) + warp * 16;
+    if (lane == 0) { hint[4] = -1.0; hint[12] = -1.0; }
+    __syncwarp();
     int loff[CPL];
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
@@ -72,7 +76,7 @@ __global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__
         for (int j = 0; j < CPL; ++j) {
             int i = lane * CPL + j;
             H[j] = (i < N) ? P.u[(size_t)i * M + col] : 0.0;
-            T[j] = H[j] / P.ch_w;
+            T[j] = H[j] * inv_chw;                  // Newton seed (soil_heat.jl:127); FreeWater overwrites it
             W[j] = 0.0;
         }
         double t = P.t[col], dt = P.dt[col];
@@ -80,8 +84,20 @@ __global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__
         int status = 0;
         long long nsteps = 0, niter = 0;
         ForcingCursor ctop, cbot;
-        if (P.top.kind == 2) forcing_seek(P.top, ctop, fmin(fmax(t, __ldg(P.top.t)), __ldg(P.top.t + P.top.n - 1)));
-        if (P.bot.kind == 2 && !P.bot_value) forcing_seek(P.bot, cbot, fmin(fmax(t, __ldg(P.bot.t)), __ldg(P.bot.t + P.bot.n - 1)));
+        // the columns of an ensemble usually sit at the same time: reuse the previous column's starting cursor when it
+        // brackets t (no global loads), else seek
+        auto start_cursor = [&](const Forcing& F, ForcingCursor& c, double* hn) {
+            if (hn[4] >= 0.0 && hn[0] <= t && t < hn[1]) {
+                c.ta = hn[0]; c.tb = hn[1]; c.ya = hn[2]; c.yb = hn[3]; c.idx = (int)hn[4];
+            } else {
+                forcing_seek(F, c, fmin(fmax(t, __ldg(F.t)), __ldg(F.t + F.n - 1)));
+                __syncwarp();
+                if (lane == 0) { hn[0] = c.ta; hn[1] = c.tb; hn[2] = c.ya; hn[3] = c.yb; hn[4] = (double)c.idx; }
+                __syncwarp();
+            }
+        };
+        if (P.top.kind == 2) start_cursor(P.top, ctop, hint);
+        if (P.bot.kind == 2 && !P.bot_value) start_cursor(P.bot, cbot, hint + 8);
 
         // device-side saveat: the column is carried through all save times of the launch in registers
         for (int kt = 0; kt < TG.n && !(status & 6); ++kt) {
@@ -246,8 +262,11 @@ __global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__
             if (i < N) P.u[(size_t)i * M + col] = H[j];
         }
         if (lane == 0) {
-            P.t[col] = t; P.dt[col] = dt; P.steps[col] += nsteps; P.iters[col] += niter;
-            if (status) P.status[col] |= status;
+            P.t[col] = t; P.dt[col] = dt;
+            // counters through RED (no load -> no stall at the end of the column)
+            atomicAdd(reinterpret_cast<unsigned long long*>(P.steps + col), (unsigned long long)nsteps);
+            atomicAdd(reinterpret_cast<unsigned long long*>(P.iters + col), (unsigned long long)niter);
+            if (status) atomicOr(P.status + col, status);
         }
     }
 }
@@ -259,7 +278,7 @@ static int lite_warp_launch_b(cgb_handle* h, const cgb::FastTargets& tg, double*
 {
     using namespace cgb;
     auto kern = k_lite_warp<CPL, MODE, MINB>;
-    size_t smem = (size_t)(5 * CPL * 32 + 4 * h->nl * LC_STRIDE) * sizeof(double);
+    size_t smem = (size_t)(5 * CPL * 32 + 4 * h->nl * LC_STRIDE + 4 * 16) * sizeof(double);
     int blocks_per_sm = 0;
     CUDA_TRY(h, cgb_prepare_kernel(h, (const void*)kern, smem, &blocks_per_sm));
     long long grid = std::min<long long>((h->M + 3) / 4, (long long)h->num_sms * blocks_per_sm);
