@@ -251,6 +251,15 @@ __device__ __forceinline__ double warp_min(double v)
     return v;
 }
 
+// min over the warp of a POSITIVE double (or +inf): order of the bit patterns == order of the values
+__device__ __forceinline__ double warp_min_pos(double v)
+{
+    unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    unsigned mhi = __reduce_min_sync(FULL, hi);
+    unsigned mlo = __reduce_min_sync(FULL, hi == mhi ? lo : 0xffffffffu);
+    return __hiloint2double((int)mhi, (int)mlo);
+}
+
 // Gridded(Linear) evaluation: i = searchsortedlast clamped, w = (x-x_i)/(x_{i+1}-x_i), (1-w) y_i + w y_{i+1}
 __device__ __forceinline__ double lerp_table(const double* __restrict__ xk, const double* __restrict__ yk, int nk, double x)
 {

@@ -13,15 +13,6 @@
 
 namespace cgb {
 
-// min over the warp of a POSITIVE double (or +inf): order of the bit patterns == order of the values
-__device__ __forceinline__ double warp_min_pos(double v)
-{
-    unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
-    unsigned mhi = __reduce_min_sync(FULL, hi);
-    unsigned mlo = __reduce_min_sync(FULL, hi == mhi ? lo : 0xffffffffu);
-    return __hiloint2double((int)mhi, (int)mlo);
-}
-
 template <int CPL, int MODE>
 struct StageA {
     // H -> T, θw, kc for the CPL cells of a lane, plus dH/dT where it is used (MODE 0/2: Newton predictor; deriv: CFL limiter)

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(128) k_salt_euler(const __grid_constant__ Dev 
         sDk[s] = cell ? P.dk[i] : 1.0;
         sW1[s] = edge ? P.eW1[i] : 1.0;
         sW2[s] = edge ? P.eW2[i] : 1.0;
-        sG[s] = edge ? P.eG[i] : 0.0;
+        sG[s] = edge ? P.eG[i] / (P.eW1[i] + P.eW2[i]) : 0.0;      // 1/Δxc of the upper edge (0: not an interior edge)
     }
     __syncthreads();
     const int jb = (N - 1) - lane * CPL;
@@ -45,6 +45,9 @@ __global__ void __launch_bounds__(128) k_salt_euler(const __grid_constant__ Dev 
     const double TmK0 = S.Tm + 273.15;
     const double Lf = P.Lsl * P.rho_w;
     const double dTm_dc = TmK0 / Lf * (-P.R * TmK0);
+    // warp-uniform quotients hoisted out of the step loop; the per-cell divisions below go through rcp_fast (correctly
+    // rounded reciprocal, then one multiply: <= 1.5 ulp from the IEEE quotient)
+    const double q0 = TmK0 / Lf, gl = P.g / P.Lsl, Lg = P.Lsl / P.g, inv_tau = 1.0 / S.tau;
     // static per-cell constants (porosity profile is shared by all columns)
     double por[CPL], psi0[CPL], thwi[CPL], Cb[CPL], Kb[CPL];
     {
@@ -88,26 +91,27 @@ __global__ void __launch_bounds__(128) k_salt_euler(const __grid_constant__ Dev 
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
                 // DallAmicoSalt: freezing point depression, then Dall'Amico (FreezeCurves.jl; parity unpinned)
-                double TmK = TmK0 + TmK0 / Lf * (-P.R * c[j] * TmK0);
-                double gT = P.g / P.Lsl * psi0[j];
+                double TmK = TmK0 + q0 * (-P.R * c[j] * TmK0);
+                double gT = gl * psi0[j];
                 double Tstar = TmK + gT * TmK;
                 double dTstar_dc = dTm_dc * (1.0 + gT);
                 double TK = T[j] + 273.15;
                 double psi, dpsi_dT, dpsi_dc;
                 if (Tstar - TK >= 0.0) {
-                    double cfac = P.Lsl / (P.g * Tstar);
+                    double rT = rcp_fast(Tstar);
+                    double cfac = Lg * rT;
                     psi = psi0[j] + cfac * (TK - Tstar);
                     dpsi_dT = cfac;
-                    dpsi_dc = P.Lsl / P.g * (-TK / (Tstar * Tstar)) * dTstar_dc;
+                    dpsi_dc = Lg * (-TK * (rT * rT)) * dTstar_dc;
                 } else { psi = psi0[j]; dpsi_dT = 0.0; dpsi_dc = 0.0; }
                 double dth;
-                double thsat = fmax(S.sat * por[j], por[j]);
+                double thsat = sel_max(S.sat * por[j], por[j]);
                 thw[j] = vg_theta(psi, thsat, S.theta_res, S.alpha, S.n, m, dth);
                 dthT[j] = dth * dpsi_dT;
                 dthc[j] = dth * dpsi_dc;
                 Cc[j] = fma(dC, thw[j], Cb[j]);
                 dHdT[j] = Cc[j] + P.L * dthT[j];                    // salt_diffusion.jl:26
-                dsm[j] = S.ds0 * thw[j] / S.tau;                    // salt_diffusion.jl:28
+                dsm[j] = (S.ds0 * thw[j]) * inv_tau;                // salt_diffusion.jl:28
                 double s = fma(dK, thw[j], Kb[j]);
                 kc[j] = s * s;
             }
@@ -121,14 +125,13 @@ __global__ void __launch_bounds__(128) k_salt_euler(const __grid_constant__ Dev 
                 double T1 = (j == 0) ? Tup : T[j - 1], c1 = (j == 0) ? cup : c[j - 1];
                 double k1 = (j == 0) ? kup : kc[j - 1], d1 = (j == 0) ? dup : dsm[j - 1];
                 int s = j * 32 + lane;
-                double w1 = sW1[s], w2 = sW2[s], g = sG[s];
-                // harmonicmean + flux (math.jl:41,141) -- true divisions: this kernel is dominated by pow()
-                ke[j] = (w1 + w2) / (w1 * (1.0 / k1) + w2 * (1.0 / kc[j]));
-                de[j] = (w1 + w2) / (w1 * (1.0 / d1) + w2 * (1.0 / dsm[j]));
-                double idx = g / (w1 + w2);                          // 1/Δxc
-                jH[j] = -ke[j] * (T[j] - T1) * idx;
+                double w1 = sW1[s], w2 = sW2[s], idx = sG[s];        // idx = 1/Δxc
+                // harmonicmean (math.jl:41): (w1+w2)/(w1/k1 + w2/k2) = (w1+w2) k1 k2 / (w1 k2 + w2 k1), one reciprocal each
+                ke[j] = ((w1 + w2) * (k1 * kc[j])) * rcp_fast(fma(w1, kc[j], w2 * k1));
+                de[j] = ((w1 + w2) * (d1 * dsm[j])) * rcp_fast(fma(w1, dsm[j], w2 * d1));
+                jH[j] = -ke[j] * (T[j] - T1) * idx;                  // math.jl:141
                 jc[j] = -de[j] * (c[j] - c1) * idx;
-                if (g == 0.0) { jH[j] = 0.0; jc[j] = 0.0; }
+                if (idx == 0.0) { jH[j] = 0.0; jc[j] = 0.0; }
             }
             if (lane == 0) {
                 ke[0] = kc[0]; de[0] = dsm[0];
@@ -150,14 +153,18 @@ __global__ void __launch_bounds__(128) k_salt_euler(const __grid_constant__ Dev 
                 double A = dHdT[j], B = P.L * dthc[j], Dd = dHv[j];
                 double E = thw[j] + c[j] * dthc[j], F = c[j] * dthT[j], Gg = dcF[j];
                 double det = A * E - B * F;
-                dTv[j] = (-B * Gg + Dd * E) / det;
-                dcv[j] = (-F * Dd + A * Gg) / det;
+                double rdet = rcp_fast(det);
+                dTv[j] = (-B * Gg + Dd * E) * rdet;
+                dcv[j] = (-F * Dd + A * Gg) * rdet;
                 if (lane * CPL + j < N) {
                     double dx = sDk[s];
-                    double dts = S.courant * (1.0 / de[j]) * (dx * dx);                         // salt_diffusion.jl:112-119
-                    lim = fmin(fmin(lim, dts), S.dc_max / fabs(dcv[j]));
-                    double dth = S.heat_courant * (dHdT[j] / kc[j]) * (dx * dx);                // heat_conduction.jl:170-178
-                    limh = fmin(limh, dth);
+                    double dts = S.courant * rcp_fast(de[j]) * (dx * dx);                       // salt_diffusion.jl:112-119
+                    double adc = fabs(dcv[j]);
+                    double dtc = (adc > 0.0) ? S.dc_max * rcp_fast(adc) : INFINITY;              // dc_max/|dc| (Inf for dc == 0)
+                    if (dts < lim) lim = dts;                                                   // NaN is skipped, as by fmin
+                    if (dtc < lim) lim = dtc;
+                    double dth = S.heat_courant * (dHdT[j] * rcp_fast(kc[j])) * (dx * dx);      // heat_conduction.jl:170-178
+                    if (dth < limh) limh = dth;
                 }
             }
             if (DIAG) {
@@ -196,14 +203,16 @@ __global__ void __launch_bounds__(128) k_salt_euler(const __grid_constant__ Dev 
             for (int j = 0; j < CPL; ++j) { T[j] = fma(dt, dTv[j], T[j]); c[j] = fma(dt, dcv[j], c[j]); }
             t = t + dt;
             ++nsteps;
-            lim = warp_min(lim);
-            limh = warp_min(limh);
-            if (!isfinite(limh)) limh = INFINITY;
-            lim = fmin(lim, limh);
-            if (!(lim > 0.0)) status |= 8;
-            double dtn = fmax(fmin(lim, P.dtmax), P.dtmin);
-            if (t < t_target) dtn = fmin(dtn, t_target - t);
-            dt = fmin(P.dtmax, dtn);
+            // warp minima through the integer REDUX unit (positive doubles order like their bit patterns); a non-positive or
+            // NaN limit is the reference's "dt <= 0" assertion (tile.jl:174)
+            const bool bad = __any_sync(FULL, !(lim > 0.0) || !(limh > 0.0));
+            lim = warp_min_pos(lim > 0.0 ? lim : INFINITY);
+            limh = warp_min_pos(limh > 0.0 ? limh : INFINITY);
+            lim = sel_min(lim, limh);
+            if (bad) { status |= 8; lim = 0.0; }
+            double dtn = sel_max(sel_min(lim, P.dtmax), P.dtmin);
+            if (t < t_target) dtn = sel_min(dtn, t_target - t);
+            dt = sel_min(dtn, P.dtmax);
         }
         if (!DIAG) {
 #pragma unroll
@@ -212,8 +221,9 @@ __global__ void __launch_bounds__(128) k_salt_euler(const __grid_constant__ Dev 
                 if (i < N) { P.u[(size_t)i * M + col] = T[j]; P.u[(size_t)(N + i) * M + col] = c[j]; }
             }
             if (lane == 0) {
-                P.t[col] = t; P.dt[col] = dt; P.steps[col] += nsteps;
-                if (status) P.status[col] |= status;
+                P.t[col] = t; P.dt[col] = dt;
+                atomicAdd(reinterpret_cast<unsigned long long*>(P.steps + col), (unsigned long long)nsteps);
+                if (status) atomicOr(P.status + col, status);
             }
         }
     }
