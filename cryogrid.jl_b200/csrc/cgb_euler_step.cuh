@@ -34,11 +34,9 @@ struct StageA {
     }
 };
 
-#ifdef CGB_EULER_MINB
-#define CGB_STEP_BOUNDS __launch_bounds__(128, CGB_EULER_MINB)
-#else
-#define CGB_STEP_BOUNDS __launch_bounds__(128)
-#endif
+// 3 resident CTAs (12 warps) per SM = 168 registers up to 9 cells per lane: measured faster than 2 CTAs with ~200 registers
+// and than 4 CTAs with 128 registers + spills; deeper grids (10..16 cells per lane) get 2 CTAs x 255 registers
+#define CGB_STEP_BOUNDS __launch_bounds__(128, (CPL <= 9 ? 3 : 2))
 
 template <int CPL, int MODE>
 __global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, const __grid_constant__ FastTargets TG, Diag D)
