@@ -18,7 +18,12 @@ import cryogrid_jl_b200 as cg  # noqa: E402
 DAY = 86400.0
 
 
+MAX_LAUNCHES = 0
+
+
 def timed(eng, targets):
+    if MAX_LAUNCHES:
+        targets = list(targets)[:MAX_LAUNCHES]
     eng.profile_enable(True); eng.profile_read()
     s0 = eng.stats()
     t0 = time.perf_counter()
@@ -45,7 +50,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--only", default="")
+    ap.add_argument("--launches", type=int, default=0, help="time only the first N launches of every configuration (ncu captures)")
     args = ap.parse_args()
+    global MAX_LAUNCHES
+    MAX_LAUNCHES = args.launches
     out = []
     only = set(args.only.split(",")) if args.only else None
 

@@ -186,7 +186,11 @@ int cgb_get_diag(cgb_handle* h, const char* var, double t, double* out);
  * BEFORE it applies u += dt*du (basic_solvers.jl:61-66); LiteImplicit's last evaluation is the start of its last Picard
  * iteration (cglite_step.jl:45-62).  So the reference's saved T, θw belong to the state one step (one iteration) before the
  * saved H.  "T"/"thw" reproduce exactly that (the stepping kernel writes them on the last step of each interval, no extra
- * launch); "T_now"/"thw_now" are recomputed from the saved state itself; "H" is the prognostic state at the save time. */
+ * launch); "T_now"/"thw_now" are recomputed from the saved state itself; "H" is the prognostic state at the save time.
+ * When only "T"/"thw" are requested and tsave is strictly increasing, up to 8 save times share one kernel launch (a column
+ * stays in registers across them; CGEuler, all freeze curves, and LiteImplicitEuler); otherwise one launch per save time.
+ * With the on-device Newton solver the two schedules agree to the solver tolerance (1e-9 K), not bitwise: a running column
+ * carries its Newton seed, a fresh launch restarts it from H/c_w (soil_heat.jl:127). */
 int cgb_solve_saveat(cgb_handle* h, const double* tsave, int64_t nsave, const char* vars, double* out);
 
 /* Device-side output path: like cgb_solve_saveat, but only the cells cell_index[0..nsel) are kept --

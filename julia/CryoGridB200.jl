@@ -101,6 +101,19 @@ function SciMLBase.__solve(ensprob::SciMLBase.EnsembleProblem, alg::CryoGridODEA
     return res   # a maintainer would wrap res.out[i, :, :, :] into CryoGridOutput per member here
 end
 
+# Optional entry points (same handle `h`, before cgb_destroy):
+#   on-device initial condition instead of cgb_set_state (initializers.jl:42-67 / Heat/heat_init.jl:58-85):
+#     ccall((:cgb_init_interp, libcgb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int32, Float64), h, zk, Tk, nk, 0, t0)
+#     ccall((:cgb_init_steadystate, libcgb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32, Float64, Int32, Float64, Float64),
+#           h, T0, per, Qgeo, maxiters, thresh, t0)
+#   device-side output path: selected cells of every saved variable + Diagnostics.thawdepth per column and save time
+#     ccall((:cgb_solve_saveat_select, libcgb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Cstring, Ptr{Int32}, Int32, Ptr{Float64}, Ptr{Float64}),
+#           h, tsave, nsave, "T,thw", Int32.(cells .- 1), length(cells), out_sel, out_thaw)
+#   ensemble moments without moving the fields (per-cell sum x and sum x^2 over the columns of this handle):
+#     ccall((:cgb_ensemble_partial, libcgb), Cint, (Ptr{Cvoid}, Cstring, Float64, Ptr{Float64}, Ptr{Float64}), h, "T", t, s1, s2)
+# Saved "T"/"thw" are the reference's saved values (the diagnostic cache of the last RHS evaluation of the interval, one step
+# behind the saved "H"); "T_now"/"thw_now" are recomputed from the saved state (INTEGRATION.md).
+
 # --- helpers a maintainer fills in from CryoGrid internals (Stratigraphy / Tile accessors) ---
 function flatten_layers end      # per-cell 0-based layer index from Tiles.layeridx (src/Tiles/state.jl:91-131)
 function soilpara end            # SimpleSoil of layer l (src/Physics/Soils/para/simple.jl:8-15)
