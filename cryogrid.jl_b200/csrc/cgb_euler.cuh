@@ -1,4 +1,6 @@
-// cgb_euler.cuh -- fused diagnostic + flux + Euler + adaptive-dt kernel (explicit enthalpy heat).
+// cgb_euler.cuh -- device functions of the explicit enthalpy-heat path (layer constants, freeze curves, SFCC lookup /
+// Newton, forcing) and the one-evaluation diagnostics kernel k_heat_diag; the stepping kernels are in
+// cgb_euler_step.cuh (any freeze curve) and cgb_euler_fast.cuh (FreeWater).  Execution model of all of them:
 //
 // One WARP owns one column; lane l holds cells [l*CPL, (l+1)*CPL) of H in REGISTERS for the whole
 // save interval, so a column is read from HBM once per cgb_advance_to and written once, however many
@@ -8,7 +10,7 @@
 //   edge conductivity + flux        harmonic mean folded into one reciprocal (math.jl:41,141)
 //   boundary fluxes                 heat_bc.jl:9-35, methods.jl:156
 //   divergence + Euler update       math.jl:68, basic_solvers.jl:66
-//   max|dH| -> next dt              butterfly shuffle; heat_conduction.jl:183-191, basic_solvers.jl:76-77,
+//   max|dH| -> next dt              REDUX / shuffles; heat_conduction.jl:183-191, basic_solvers.jl:76-77,
 //                                   integrator.jl:126-131 (clip to the save time)
 // Neighbour cells across lanes travel by __shfl_up/down.  Static grid constants and the per-(column,layer)
 // soil constants live in shared memory ([slot][lane] layout: conflict-free).  Warps fetch columns from a
@@ -309,18 +311,15 @@ __device__ __forceinline__ double forcing_eval(const Forcing& F, ForcingCursor& 
 }
 
 // -------------------------------------------------------------------------------------------------
-#ifdef CGB_EULER_MINB
-#define CGB_EULER_BOUNDS __launch_bounds__(128, CGB_EULER_MINB)
-#else
-#define CGB_EULER_BOUNDS __launch_bounds__(128)
-#endif
-template <int CPL, int MODE, bool DIAG>
-__global__ void CGB_EULER_BOUNDS k_heat_euler(const __grid_constant__ Dev P, double t_target, Diag D)
+// One RHS evaluation at the current state and time t: every diagnostic the reference caches (T, θw, C, ∂H∂T, ∂θw∂T, kc, k,
+// jH, dH) for cgb_rhs / cgb_get_diag / the "*_now" saved variables.  Any freeze curve / solver (generic cell function with
+// the fully converged Newton: bitwise the oracle's procedure).  The state is not modified.
+template <int CPL>
+__global__ void __launch_bounds__(128) k_heat_diag(const __grid_constant__ Dev P, double t, Diag D)
 {
     extern __shared__ double smem[];
     double* sInvDk = smem;
-    double* sDk = sInvDk + CPL * 32;
-    double* sW1 = sDk + CPL * 32;
+    double* sW1 = sInvDk + CPL * 32;
     double* sW2 = sW1 + CPL * 32;
     double* sG = sW2 + CPL * 32;
     double* sLCall = sG + CPL * 32;
@@ -336,7 +335,6 @@ __global__ void CGB_EULER_BOUNDS k_heat_euler(const __grid_constant__ Dev P, dou
         int i = ln * CPL + j;
         bool cell = i < N, edge = (i > 0 && i < N);
         sInvDk[s] = cell ? P.inv_dk[i] : 0.0;
-        sDk[s] = cell ? P.dk[i] : 1.0;
         sW1[s] = edge ? P.eW1[i] : 1.0;
         sW2[s] = edge ? P.eW2[i] : 1.0;
         sG[s] = edge ? P.eG[i] : 0.0;
@@ -364,159 +362,71 @@ __global__ void CGB_EULER_BOUNDS k_heat_euler(const __grid_constant__ Dev P, dou
         __syncwarp();
         stage_layer_consts(P, col, lcw, lane);
         __syncwarp();
-        const bool n2 = (MODE == 1) && all_layers_n2(P, lcw, lane);
 
-        double H[CPL], T[CPL];
-#pragma unroll
-        for (int j = 0; j < CPL; ++j) {
-            int i = lane * CPL + j;
-            H[j] = (i < N) ? P.u[(size_t)i * M + col] : 0.0;
-            T[j] = H[j] / P.ch_w;   // Newton seed (soil_heat.jl:127)
-        }
-        double t = DIAG ? t_target : P.t[col];
-        double dt = P.dt[col];
-        const double nf = P.nf[col], nt = P.nt[col], toff = P.top_offset[col];
+        // ---- boundary values at t (basic_solvers.jl:61-63)
         int status = 0;
-        long long nsteps = 0;
         ForcingCursor ctop, cbot;
         if (P.top.kind == 2) forcing_seek(P.top, ctop, fmin(fmax(t, __ldg(P.top.t)), __ldg(P.top.t + P.top.n - 1)));
         if (P.bot.kind == 2 && !P.bot_value) forcing_seek(P.bot, cbot, fmin(fmax(t, __ldg(P.bot.t)), __ldg(P.bot.t + P.bot.n - 1)));
+        double vtop = forcing_eval(P.top, ctop, t, status) + P.top_offset[col];
+        if (P.top_kind == 0 && P.use_nfactor) vtop = ((vtop <= 0.0) ? P.nf[col] : P.nt[col]) * vtop;   // heat_bc.jl:78-86
+        const double vbot = P.bot_value ? P.bot_value[col] : forcing_eval(P.bot, cbot, t, status);
 
-        while (DIAG || t < t_target) {
-            // ---- boundary values at the START of the step (basic_solvers.jl:61-63)
-            double vtop = forcing_eval(P.top, ctop, t, status) + toff;
-            if (P.top_kind == 0 && P.use_nfactor) vtop = ((vtop <= 0.0) ? nf : nt) * vtop;   // heat_bc.jl:78-86
-            double vbot = P.bot_value ? P.bot_value[col] : forcing_eval(P.bot, cbot, t, status);
-
-            // ---- stage A: H -> T, θw, C, kc
-            double kc[CPL], thw[CPL], C[CPL], dHdT[CPL], dth[CPL];
-            if (MODE == 1) {
-                stage_a_lut<CPL>(P, lcw, loff, H, T, thw, C, dHdT, dth, kc, dC, dK, n2);
-            } else {
+        // ---- H -> T, θw, C, dH/dT, dθw/dT, kc
+        double T[CPL], kc[CPL], thw[CPL], C[CPL], dHdT[CPL], dth[CPL];
 #pragma unroll
-                for (int j = 0; j < CPL; ++j)
-                    freezethaw_cell<MODE, DIAG>(P, lcw + loff[j], H[j], dC, dK, T[j], thw[j], C[j], dHdT[j], dth[j], kc[j]);
-            }
-
-            if (!DIAG && (D.T || D.thw) && !(t + dt < t_target)) {
-                // last step of the interval: the reference saves the diagnostics cached by this RHS evaluation (state BEFORE
-                // the step): problem.jl:67-68, Numerics/statevars.jl:81-106, basic_solvers.jl:61-66
-#pragma unroll
-                for (int j = 0; j < CPL; ++j) {
-                    int i = lane * CPL + j;
-                    if (i < N) {
-                        if (D.T) D.T[(size_t)i * M + col] = T[j];
-                        if (D.thw) D.thw[(size_t)i * M + col] = thw[j];
-                    }
-                }
-            }
-            // ---- stage B/C: edge fluxes (upper edge of every local cell)
-            double Tup = __shfl_up_sync(FULL, T[CPL - 1], 1);
-            double kup = __shfl_up_sync(FULL, kc[CPL - 1], 1);
-            double je[CPL + 1];
-            double ke[CPL];   // DIAG only
-#pragma unroll
-            for (int j = 0; j < CPL; ++j) {
-                double T1 = (j == 0) ? Tup : T[j - 1];
-                double k1 = (j == 0) ? kup : kc[j - 1];
-                int s = j * 32 + lane;
-                double w1 = sW1[s], w2 = sW2[s];
-                double den = fma(w2, k1, w1 * kc[j]);
-                double r = rcp_fast(den);
-                double kk = k1 * kc[j];
-                je[j] = -(((T[j] - T1) * kk) * sG[s]) * r;
-                if (DIAG) ke[j] = (kk * (w1 + w2)) * r;
-            }
-            if (lane == 0) {
-                // Top: Dirichlet -k[1](T[1]-T_ub)/(Δk[1]/2)  (heat_bc.jl:9-17) ; Neumann: value (methods.jl:156)
-                je[0] = (P.top_kind == 0) ? -(kc[0] * (T[0] - vtop)) * P.ctop : vtop;
-                if (DIAG) ke[0] = kc[0];
-            }
-            je[CPL] = __shfl_down_sync(FULL, je[0], 1);
-            // ---- divergence, limiter reduction, Euler update
-            double maxabs = 0.0, mincfl = INFINITY;
-            double dH[CPL];
-#pragma unroll
-            for (int j = 0; j < CPL; ++j) {
-                double jlow = je[j + 1];
-                if (j == jb) {
-                    // Bottom: Dirichlet -k[end](T_lb-T[end])/(Δk[end]/2) (heat_bc.jl:18-27) ; Neumann: value
-                    jlow = (P.bot_kind == 0) ? -(kc[j] * (vbot - T[j])) * P.cbot : vbot;
-                    je[j + 1] = jlow;
-                }
-                int s = j * 32 + lane;
-                dH[j] = (je[j] - jlow) * sInvDk[s];
-                double a = fabs(dH[j]);
-                maxabs = (a > maxabs) ? a : maxabs;                       // fmax() is ~7 instructions on sm_100; NaN is skipped as by fmax
-                if (P.limiter == 1) {
-                    double dx = sDk[s];
-                    double v = dHdT[j] * rcp_fast(kc[j]);
-                    double c = P.courant * v * (dx * dx);
-                    if (lane * CPL + j < N) mincfl = fmin(mincfl, c);
-                }
-            }
-            if (DIAG) {
-#pragma unroll
-                for (int j = 0; j < CPL; ++j) {
-                    int i = lane * CPL + j;
-                    if (i < N) {
-                        size_t o = (size_t)i * M + col;
-                        if (D.T) D.T[o] = T[j];
-                        if (D.thw) D.thw[o] = thw[j];
-                        if (D.C) D.C[o] = C[j];
-                        if (D.dHdT) D.dHdT[o] = dHdT[j];
-                        if (D.dthwdT) D.dthwdT[o] = dth[j];
-                        if (D.kc) D.kc[o] = kc[j];
-                        if (D.dH) D.dH[o] = dH[j];
-                        if (D.k) D.k[o] = ke[j];
-                        if (D.jH) D.jH[o] = je[j];
-                        if (i == N - 1) {
-                            size_t ob = (size_t)N * M + col;
-                            if (D.k) D.k[ob] = kc[j];
-                            if (D.jH) D.jH[ob] = je[j + 1];
-                        }
-                    }
-                }
-                break;
-            }
-            maxabs = warp_max(maxabs);
-#pragma unroll
-            for (int j = 0; j < CPL; ++j) {
-                double inc = dt * dH[j];
-                H[j] += inc;                                              // u += dt*du (basic_solvers.jl:66)
-                if (MODE == 0 || MODE == 2) T[j] = fma(inc, rcp_fast(dHdT[j]), T[j]);   // first-order predictor = next Newton seed
-            }
-            t = t + dt;
-            ++nsteps;
-            // ---- next dt: timestep() from the OLD du (basic_solvers.jl:76-77), then saveat! clip
-            double lim = P.maxdelta / maxabs;                             // = min_i |Δmax/dH_i| (steplimiters.jl:15-18)
-            if (!isfinite(lim)) lim = INFINITY;
-            if (P.limiter == 1) {
-                mincfl = warp_min(mincfl);
-                lim = fmin(lim, mincfl);
-                if (!isfinite(lim)) lim = INFINITY;                      // heat_conduction.jl:180
-            } else {
-                if (!(lim > 0.0)) lim = INFINITY;                        // heat_conduction.jl:189
-            }
-            if (!(lim > 0.0)) status |= 8;                                // tile.jl:174
-            double dtn = sel_max(sel_min(lim, P.dtmax), P.dtmin);
-            if (t < t_target) dtn = sel_min(dtn, t_target - t);          // integrator.jl:126-131
-            dt = sel_min(dtn, P.dtmax);                                   // integrator.jl:89
-            if (status & 4) break;
+        for (int j = 0; j < CPL; ++j) {
+            int i = lane * CPL + j;
+            double H = (i < N) ? P.u[(size_t)i * M + col] : 0.0;
+            T[j] = H / P.ch_w;   // Newton seed (soil_heat.jl:127)
+            freezethaw_generic<true>(P, lcw + loff[j], H, dC, dK, T[j], thw[j], C[j], dHdT[j], dth[j], kc[j]);
         }
-        if (!DIAG) {
+        // ---- edge conductivities and fluxes (upper edge of every local cell)
+        double Tup = __shfl_up_sync(FULL, T[CPL - 1], 1);
+        double kup = __shfl_up_sync(FULL, kc[CPL - 1], 1);
+        double je[CPL + 1], ke[CPL];
 #pragma unroll
-            for (int j = 0; j < CPL; ++j) {
-                int i = lane * CPL + j;
-                if (i < N) P.u[(size_t)i * M + col] = H[j];
-            }
-            if (lane == 0) {
-                P.t[col] = t;
-                P.dt[col] = dt;
-                P.steps[col] += nsteps;
-                if (status) P.status[col] |= status;
+        for (int j = 0; j < CPL; ++j) {
+            double T1 = (j == 0) ? Tup : T[j - 1];
+            double k1 = (j == 0) ? kup : kc[j - 1];
+            int s = j * 32 + lane;
+            double w1 = sW1[s], w2 = sW2[s];
+            double r = rcp_fast(fma(w2, k1, w1 * kc[j]));
+            double kk = k1 * kc[j];
+            je[j] = -(((T[j] - T1) * kk) * sG[s]) * r;
+            ke[j] = (kk * (w1 + w2)) * r;
+        }
+        if (lane == 0) {
+            // Top: Dirichlet -k[1](T[1]-T_ub)/(Δk[1]/2)  (heat_bc.jl:9-17) ; Neumann: value (methods.jl:156)
+            je[0] = (P.top_kind == 0) ? -(kc[0] * (T[0] - vtop)) * P.ctop : vtop;
+            ke[0] = kc[0];
+        }
+        je[CPL] = __shfl_down_sync(FULL, je[0], 1);
+        // ---- divergence and output
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            // Bottom: Dirichlet -k[end](T_lb-T[end])/(Δk[end]/2) (heat_bc.jl:18-27) ; Neumann: value
+            if (j == jb) je[j + 1] = (P.bot_kind == 0) ? -(kc[j] * (vbot - T[j])) * P.cbot : vbot;
+            int i = lane * CPL + j;
+            if (i < N) {
+                size_t o = (size_t)i * M + col;
+                if (D.T) D.T[o] = T[j];
+                if (D.thw) D.thw[o] = thw[j];
+                if (D.C) D.C[o] = C[j];
+                if (D.dHdT) D.dHdT[o] = dHdT[j];
+                if (D.dthwdT) D.dthwdT[o] = dth[j];
+                if (D.kc) D.kc[o] = kc[j];
+                if (D.dH) D.dH[o] = (je[j] - je[j + 1]) * sInvDk[j * 32 + lane];
+                if (D.k) D.k[o] = ke[j];
+                if (D.jH) D.jH[o] = je[j];
+                if (i == N - 1) {
+                    size_t ob = (size_t)N * M + col;
+                    if (D.k) D.k[ob] = kc[j];
+                    if (D.jH) D.jH[ob] = je[j + 1];
+                }
             }
         }
+        (void)status;   // a diagnostic evaluation outside the forcing range returns NaN fluxes; the column status is left alone
     }
 }
 

@@ -1,6 +1,6 @@
 // cgb_euler_fast.cuh -- the FreeWater + MaxDelta fast path of the fused CGEuler kernel (BASELINE cfg2).
 //
-// Same algorithm and data layout as k_heat_euler (cgb_euler.cuh): one warp per column, CPL cells per lane held in
+// Same algorithm and data layout as k_heat_step (cgb_euler_step.cuh): one warp per column, CPL cells per lane held in
 // registers for the whole save interval.  What differs is the arithmetic budget -- the kernel is bound by the FP64
 // pipe (64 lanes/clk/SM), so everything here minimises FP64-pipe instructions per cell-step:
 //   * one clamp serves both θw and the enthalpy inverse:  hc = clamp(H, 0, Lθ);  x = hc/Lθ;  T = (H - hc)/C

@@ -5,7 +5,7 @@
 // evaluated right after the Euler update of step k, while the warp-wide max|dH| reduction (integer REDUX unit) and the
 // reciprocal for the next dt are still in flight.  Stage A works on the CPL cells of a lane phase by phase, so the
 // table loads / transcendental chains of different cells overlap (the kernel is latency bound: 12 warps per SM).
-//   k_heat_euler<CPL, 0, true> (cgb_euler.cuh) remains the one-evaluation diagnostics kernel.
+//   k_heat_diag<CPL> (cgb_euler.cuh) is the one-evaluation diagnostics kernel.
 // Reference: basic_solvers.jl:61-77 (CGEuler step), heat_conduction.jl:18-57,150-191, soil_heat.jl:116-140,
 // heat_bc.jl:9-35,78-86, steplimiters.jl:15-18, integrator.jl:89,126-131, problem.jl:67-68 (what a save stores).
 #pragma once
