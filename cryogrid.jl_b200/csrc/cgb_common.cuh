@@ -35,7 +35,12 @@ enum LayerConst {
     LC_HMIN,       // first knot
     LC_HMAX,       // last knot
     LC_INVBW,      // nb / (Hmax - Hmin)
-    LC_NBM1        // nb - 1 (as double: clamp bound of the bucket index)
+    LC_NBM1,       // nb - 1 (as double: clamp bound of the bucket index)
+    // layers solved by the on-device Newton iteration reuse the table slots:
+    LC_NW_HSTAR = LC_HMIN,    // enthalpy at the kink T = T* (everything above is thawed: closed form)
+    LC_NW_THU = LC_HMAX,      // θw of the thawed branch, θ(ψ0)
+    LC_NW_CU = LC_INVBW,      // heat capacity of the thawed branch
+    LC_NW_TSTARC = LC_NBM1    // T* in °C
 };
 
 struct Forcing {

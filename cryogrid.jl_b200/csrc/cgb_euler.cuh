@@ -67,6 +67,14 @@ __device__ __forceinline__ void layer_consts(const Dev& P, long long col, int l,
             reinterpret_cast<int*>(c + LC_BOFF)[0] = P.lut_boff[id];
             double hmin = P.lutH[off], hmax = P.lutH[off + nk - 1], nb = (double)P.lut_nb[id];
             c[LC_HMIN] = hmin; c[LC_HMAX] = hmax; c[LC_INVBW] = nb / (hmax - hmin); c[LC_NBM1] = nb - 1.0;
+        } else {
+            // the thawed branch (T >= T*) is linear in T: θw = θ(ψ0), C = C(θw); its lower end is the kink enthalpy H*
+            double dth;
+            double thu = vg_theta(psi0, thsat_e, thres, alpha, n, c[LC_M], dth);
+            double Cu = fma(P.ch_w - P.ch_i, thu, c[LC_CBS]);
+            double TstarC = Tstar - 273.15;
+            c[LC_NW_THU] = thu; c[LC_NW_CU] = Cu; c[LC_NW_TSTARC] = TstarC;
+            c[LC_NW_HSTAR] = TstarC * Cu + P.L * thu;
         }
     }
 }
@@ -84,16 +92,27 @@ __device__ __forceinline__ bool all_layers_n2(const Dev& P, const double* lcw, i
     return __all_sync(FULL, ok);
 }
 
-// Safeguarded Newton for T*C(θw(T)) + Lθw(T) = H (monotone in T; same bracketing as the oracle).
-// EXACT: iterate to 1e-15 relative and re-evaluate θw at the root (diagnostics: bitwise-comparable with the oracle's
-// procedure).  Otherwise (stepping): stop once |ΔT| <= 1e-9 -- Newton is quadratic, so the accepted T is accurate to
-// ~1e-15 -- and carry θw, C to the new T with a first-order correction instead of another 2-exp/2-log evaluation.
+// The freeze curve has a kink at T* (ψ stops depending on T above it), where dH/dT jumps by orders of magnitude; a Newton
+// iteration started on the wrong side needs many bracketing steps, and in a warp every lane waits for the one cell at the
+// freezing front.  So the side is decided first, exactly: H >= H(T*) is the thawed branch, which is LINEAR in T (closed
+// form, no iteration); below it the iteration runs on the smooth frozen branch only, bracketed by [-273, T*].
+// EXACT: iterate to 1e-15 relative and re-evaluate θw at the root (diagnostics; the same root as the oracle's safeguarded
+// Newton over the whole range).  Otherwise (stepping): stop once |ΔT| <= 1e-9 -- Newton is quadratic, so the accepted T is
+// accurate to ~1e-15 -- and carry θw, C to the new T with a first-order correction instead of another evaluation.
 template <bool EXACT>
 __device__ __forceinline__ void sfcc_newton_solve(const double* lc, double L, double dC, double H, double& T, double& thw,
                                                   double& C, double& dHdT, double& dth)
 {
-    double lo = -273.0, hi = 1.0e4;
-    if (!(T > lo && T < hi)) T = 0.0;
+    if (H >= lc[LC_NW_HSTAR]) {
+        thw = lc[LC_NW_THU];
+        C = lc[LC_NW_CU];
+        T = EXACT ? (H - L * thw) / C : (H - L * thw) * rcp_fast(C);
+        dth = 0.0;
+        dHdT = C;
+        return;
+    }
+    double lo = -273.0, hi = lc[LC_NW_TSTARC];
+    if (!(T > lo && T < hi)) T = hi;                   // a cell that has just crossed the kink starts at it
     for (int it = 0; it < 200; ++it) {
         thw = sfcc_theta(lc, T, dth);
         C = fma(dC, thw, lc[LC_CBS]);
@@ -102,8 +121,8 @@ __device__ __forceinline__ void sfcc_newton_solve(const double* lc, double L, do
         if (r > 0.0) hi = T; else lo = T;
         double Tn = EXACT ? T - r / dHdT : fma(-r, rcp_fast(dHdT), T);
         // a Newton step is taken if it falls strictly inside the bracket, or ON its end when it is a converged step (the
-        // strict test alone would bisect there; the inclusive test alone lets Newton 2-cycle between the bracket ends:
-        // unfrozen side -> far frozen side -> back).  NaN -> bisect.
+        // strict test alone would bisect there; the inclusive test alone lets Newton 2-cycle between the bracket ends).
+        // NaN -> bisect.
         const double tol = (EXACT ? 1e-15 : 1e-9) * fmax(1.0, fabs(Tn));
         bool small = fabs(Tn - T) <= tol;
         bool safe = (Tn > lo && Tn < hi) || (small && Tn >= lo && Tn <= hi);
