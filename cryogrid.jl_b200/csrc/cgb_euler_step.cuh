@@ -54,10 +54,17 @@ __global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, const
     const int N = P.N;
     const long long M = P.M;
     double* lcw = sLCall + warp * (P.n_layers * LC_STRIDE);
+    // Cell -> (lane, slot) mapping.  Contiguous (cell = lane*CPL + slot: neighbours mostly in the same lane) for the modes whose
+    // per-cell work is uniform.  INTERLEAVED (cell = slot*32 + lane) for the iterative modes (on-device Newton): the cells that
+    // need a second evaluation are the dynamic ones near the surface / the freezing front, i.e. neighbours; contiguous, they sit
+    // in a few lanes and every slot of the warp waits for them (measured: 2.2 evaluations per cell and warp for 1.24 per
+    // thread); interleaved, they fill whole slots, and a slot's iteration loop runs with all lanes busy or not at all.
+    constexpr bool ILV = (MODE == 0 || MODE == 2);
+    auto cell_of = [&](int ln, int j) { return ILV ? j * 32 + ln : ln * CPL + j; };
 
     for (int s = threadIdx.x; s < CPL * 32; s += blockDim.x) {
         int j = s >> 5, ln = s & 31;
-        int i = ln * CPL + j;
+        int i = cell_of(ln, j);
         bool cell = i < N, edge = (i > 0 && i < N);
         sInvDk[s] = cell ? P.inv_dk[i] : 0.0;
         sDk[s] = cell ? P.dk[i] : 1.0;
@@ -69,14 +76,15 @@ __global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, const
 
     const double dC = P.ch_w - P.ch_i;
     const double dK = P.sk_w - P.sk_i;
-    const int jb = (N - 1) - lane * CPL;   // local slot of the bottom cell (if in [0,CPL))
+    // local slot of the bottom cell (-1 / out of [0,CPL) in the lanes that do not hold it)
+    const int jb = ILV ? ((lane == ((N - 1) & 31)) ? ((N - 1) >> 5) : -1) : (N - 1) - lane * CPL;
     const bool cfl = (P.limiter == 1);
     const bool save = (D.T != nullptr) || (D.thw != nullptr);
 
     int loff[CPL];
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
-        int i = lane * CPL + j;
+        int i = cell_of(lane, j);
         loff[j] = P.cell_layer[i < N ? i : N - 1] * LC_STRIDE;
     }
 
@@ -95,7 +103,7 @@ __global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, const
         double H[CPL], T[CPL], thw[CPL], kc[CPL], dHdT[CPL];
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
-            int i = lane * CPL + j;
+            int i = cell_of(lane, j);
             H[j] = (i < N) ? P.u[(size_t)i * M + col] : 0.0;
             T[j] = H[j] / P.ch_w;   // Newton seed (soil_heat.jl:127)
         }
@@ -129,7 +137,7 @@ __global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, const
                 // the step): problem.jl:67-68, Numerics/statevars.jl:81-106, basic_solvers.jl:61-66
 #pragma unroll
                 for (int j = 0; j < CPL; ++j) {
-                    int i = lane * CPL + j;
+                    int i = cell_of(lane, j);
                     if (i < N) {
                         size_t o = (size_t)kt * TG.save_stride + (size_t)i * M + col;
                         if (D.T) D.T[o] = T[j];
@@ -144,17 +152,26 @@ __global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, const
                 for (int j = 0; j < CPL; ++j) {
                     double dx = sDk[j * 32 + lane];
                     double c = P.courant * (dHdT[j] * rcp_fast(kc[j])) * (dx * dx);
-                    if (lane * CPL + j < N && c < mincfl) mincfl = c;
+                    if (cell_of(lane, j) < N && c < mincfl) mincfl = c;
                 }
             }
             // ---- edge fluxes (upper edge of every local cell): harmonic mean folded into one reciprocal
-            double Tup = __shfl_up_sync(FULL, T[CPL - 1], 1);
-            double kup = __shfl_up_sync(FULL, kc[CPL - 1], 1);
+            double Tup = 0.0, kup = 0.0;
+            if (!ILV) { Tup = __shfl_up_sync(FULL, T[CPL - 1], 1); kup = __shfl_up_sync(FULL, kc[CPL - 1], 1); }
             double je[CPL + 1];
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
-                double T1 = (j == 0) ? Tup : T[j - 1];
-                double k1 = (j == 0) ? kup : kc[j - 1];
+                double T1, k1;
+                if (ILV) {
+                    // upper neighbour = previous lane, same slot; lane 0 takes lane 31's previous slot (one rotating shuffle)
+                    double sT = (lane == 31 && j > 0) ? T[j > 0 ? j - 1 : 0] : T[j];
+                    double sk = (lane == 31 && j > 0) ? kc[j > 0 ? j - 1 : 0] : kc[j];
+                    T1 = __shfl_sync(FULL, sT, (lane + 31) & 31);
+                    k1 = __shfl_sync(FULL, sk, (lane + 31) & 31);
+                } else {
+                    T1 = (j == 0) ? Tup : T[j - 1];
+                    k1 = (j == 0) ? kup : kc[j - 1];
+                }
                 int s = j * 32 + lane;
                 double den = fma(sW2[s], k1, sW1[s] * kc[j]);
                 double kk = k1 * kc[j];
@@ -162,12 +179,19 @@ __global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, const
             }
             // Top: Dirichlet -k[1](T[1]-T_ub)/(Δk[1]/2) (heat_bc.jl:9-17) ; Neumann: value (methods.jl:156)
             if (lane == 0) je[0] = (P.top_kind == 0) ? -(kc[0] * (T[0] - vtop)) * P.ctop : vtop;
-            je[CPL] = __shfl_down_sync(FULL, je[0], 1);
+            if (!ILV) je[CPL] = __shfl_down_sync(FULL, je[0], 1);
             // ---- divergence, Euler update, local max|dH|
             double ad[CPL];
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
-                double jlow = je[j + 1];
+                double jlow;
+                if (ILV) {
+                    // lower edge = upper edge of the next lane's cell in this slot; lane 31 takes lane 0's next slot
+                    double sj = (lane == 0) ? ((j + 1 < CPL) ? je[j + 1 < CPL ? j + 1 : j] : 0.0) : je[j];
+                    jlow = __shfl_sync(FULL, sj, (lane + 1) & 31);
+                } else {
+                    jlow = je[j + 1];
+                }
                 // Bottom: Dirichlet -k[end](T_lb-T[end])/(Δk[end]/2) (heat_bc.jl:18-27) ; Neumann: value
                 if (j == jb) jlow = (P.bot_kind == 0) ? -(kc[j] * (vbot - T[j])) * P.cbot : vbot;
                 double dH = (je[j] - jlow) * sInvDk[j * 32 + lane];
@@ -214,7 +238,7 @@ __global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, const
         }
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
-            int i = lane * CPL + j;
+            int i = cell_of(lane, j);
             if (i < N) P.u[(size_t)i * M + col] = H[j];
         }
         if (lane == 0) {
