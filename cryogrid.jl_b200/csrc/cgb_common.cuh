@@ -181,6 +181,12 @@ __device__ __forceinline__ double relu_bits(double x)
     return __hiloint2double(hi & m, lo & m);
 }
 
+// Taylor coefficients 1/13! ... 1/2!, 1, 1 of exp and 1/21, 1/19, ... 1/3 of 2 atanh(s)/s - 2 (Horner order)
+static __constant__ double CGB_EXP_C[14] = {1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07,
+                                            2.7557319223985893e-06, 2.48015873015873e-05, 1.984126984126984e-04, 1.3888888888888889e-03,
+                                            8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5, 1.0, 1.0};
+static __constant__ double CGB_LOG_C[10] = {1.0 / 21.0, 1.0 / 19.0, 1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0, 1.0 / 11.0, 1.0 / 9.0, 1.0 / 7.0, 1.0 / 5.0, 1.0 / 3.0};
+
 // exp(a) without the special-case handling of the CUDA math library (80 SASS instructions -> ~25): a is clamped to
 // [-708, 709] (results stay normal, so the power of two can be added straight into the exponent field), reduced by
 // k = rint(a log2 e) with a two-term ln 2, and evaluated with the degree-13 Taylor polynomial on |r| <= 0.3466
@@ -194,20 +200,10 @@ __device__ __forceinline__ double exp_fast(double a)
     double kd = t - MAGIC;
     double r = fma(kd, -6.93147180559945286227e-01, a);
     r = fma(kd, -2.31904681384629955842e-17, r);
-    double p = 1.6059043836821613e-10;                   // 1/13!
-    p = fma(p, r, 2.08767569878681e-09);                 // 1/12!
-    p = fma(p, r, 2.505210838544172e-08);                // 1/11!
-    p = fma(p, r, 2.755731922398589e-07);                // 1/10!
-    p = fma(p, r, 2.7557319223985893e-06);               // 1/9!
-    p = fma(p, r, 2.48015873015873e-05);                 // 1/8!
-    p = fma(p, r, 1.984126984126984e-04);                // 1/7!
-    p = fma(p, r, 1.3888888888888889e-03);               // 1/6!
-    p = fma(p, r, 8.333333333333333e-03);                // 1/5!
-    p = fma(p, r, 4.1666666666666664e-02);               // 1/4!
-    p = fma(p, r, 1.6666666666666666e-01);               // 1/3!
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
+    // coefficients from constant memory (c[bank][offset] operands): as FP64 literals each one costs two UMOVs per use
+    double p = CGB_EXP_C[0];
+#pragma unroll
+    for (int i = 1; i < 14; ++i) p = fma(p, r, CGB_EXP_C[i]);
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
 
@@ -226,16 +222,9 @@ __device__ __forceinline__ double log_pos(double x)
     double f = m - 1.0;                                  // exact
     double s = f * rcp_fast(m + 1.0);
     double z = s * s;
-    double p = 1.0 / 21.0;
-    p = fma(p, z, 1.0 / 19.0);
-    p = fma(p, z, 1.0 / 17.0);
-    p = fma(p, z, 1.0 / 15.0);
-    p = fma(p, z, 1.0 / 13.0);
-    p = fma(p, z, 1.0 / 11.0);
-    p = fma(p, z, 1.0 / 9.0);
-    p = fma(p, z, 1.0 / 7.0);
-    p = fma(p, z, 1.0 / 5.0);
-    p = fma(p, z, 1.0 / 3.0);
+    double p = CGB_LOG_C[0];
+#pragma unroll
+    for (int i = 1; i < 10; ++i) p = fma(p, z, CGB_LOG_C[i]);
     double s2 = s + s;
     double lm = fma(s2 * z, p, s2);
     double ed = (double)e;
