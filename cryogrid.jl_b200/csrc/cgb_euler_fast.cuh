@@ -166,6 +166,9 @@ __global__ void __launch_bounds__(128, MINB) k_heat_euler_fast(const __grid_cons
         stage_a();
         for (int kt = 0; kt < TG.n; ++kt) {
         const double t_target = TG.t[kt];
+        // unrolled x3: the loop-carried copies of the software pipeline (next -> current T, kc, boundary value) disappear into
+        // register renaming across the copies (47 of 399 instructions per step were moves); measured 3.52 -> 3.62e11 (x2: 3.59, x4: 3.61)
+#pragma unroll 3
         while (t < t_target) {
             if (fkind == 2 && (t < ft_first || t > ft_last)) { status |= 4; break; }     // providers.jl:30-33
             if (SAVE && !(t + dt < t_target)) {
