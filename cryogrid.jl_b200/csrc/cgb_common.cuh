@@ -245,6 +245,16 @@ __device__ __forceinline__ double warp_min(double v)
     return v;
 }
 
+// max over the warp of a NON-NEGATIVE double through the integer REDUX unit
+__device__ __forceinline__ double warp_max_nonneg(double v)
+{
+    // v >= 0 (or NaN-free by construction: fmax drops NaN): order of doubles == order of their bit patterns
+    unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    unsigned mhi = __reduce_max_sync(FULL, hi);
+    unsigned mlo = __reduce_max_sync(FULL, hi == mhi ? lo : 0u);
+    return __hiloint2double((int)mhi, (int)mlo);
+}
+
 // min over the warp of a POSITIVE double (or +inf): order of the bit patterns == order of the values
 __device__ __forceinline__ double warp_min_pos(double v)
 {

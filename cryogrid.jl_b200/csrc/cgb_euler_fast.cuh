@@ -19,15 +19,6 @@ namespace cgb {
 constexpr int FC_STRIDE = 8;   // fast-path per-(column,layer) constants
 enum FastConst { FC_LTH = 0, FC_INVLTH, FC_CB, FC_KB, FC_DCTH, FC_DKTH, FC_THWI };
 
-__device__ __forceinline__ double warp_max_nonneg(double v)
-{
-    // v >= 0 (or NaN-free by construction: fmax drops NaN): order of doubles == order of their bit patterns
-    unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
-    unsigned mhi = __reduce_max_sync(FULL, hi);
-    unsigned mlo = __reduce_max_sync(FULL, hi == mhi ? lo : 0u);
-    return __hiloint2double((int)mhi, (int)mlo);
-}
-
 template <bool CUBIC>
 __device__ __forceinline__ double rcp_sel(double a) { return CUBIC ? rcp_fast3(a) : rcp_fast(a); }
 

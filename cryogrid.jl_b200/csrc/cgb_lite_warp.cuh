@@ -20,7 +20,9 @@
 
 namespace cgb {
 
-template <int CPL, int MODE, int MINB>
+// SAVEW: keep θw of the last evaluation for the saved output (9-16 more doubles per lane; a separate instantiation so that the
+// plain stepping kernel does not carry them)
+template <int CPL, int MODE, int MINB, bool SAVEW>
 __global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__ Dev P, const __grid_constant__ FastTargets TG,
                                                          double* __restrict__ saveT, double* __restrict__ saveW)
 {
@@ -71,13 +73,13 @@ __global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__
         stage_layer_consts(P, col, lcw, lane);
         __syncwarp();
 
-        double H[CPL], H0[CPL], T[CPL], W[CPL];
+        double H[CPL], H0[CPL], T[CPL], W[SAVEW ? CPL : 1];
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
             int i = lane * CPL + j;
             H[j] = (i < N) ? P.u[(size_t)i * M + col] : 0.0;
             T[j] = H[j] * inv_chw;                  // Newton seed (soil_heat.jl:127); FreeWater overwrites it
-            W[j] = 0.0;
+            if (SAVEW) W[j] = 0.0;
         }
         double t = P.t[col], dt = P.dt[col];
         const double nf = P.nf[col], nt = P.nt[col], toff = P.top_offset[col];
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__
                 for (int j = 0; j < CPL; ++j) {
                     double thw, C, dth;
                     freezethaw_cell<MODE>(P, lcw + loff[j], H[j], dC, dK, T[j], thw, C, dHdT[j], dth, kc[j]);
-                    if (saveW) W[j] = thw;
+                    if (SAVEW) W[j] = thw;
                 }
                 // ---- kd = k_edge/dxc on the upper edge of every local cell (harmonic mean, math.jl:141)
                 double kup = __shfl_up_sync(FULL, kc[CPL - 1], 1);
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__
                         bad |= !isfinite(e);
                     }
                 }
-                emax = warp_max(em);
+                emax = warp_max_nonneg(em);                                          // em >= 0 (NaN never enters: see `bad`)
                 ++niter; ++iter;
                 if (__any_sync(FULL, bad)) { status |= 2; break; }
             }
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__
                 if (i < N) {
                     size_t o = (size_t)kt * TG.save_stride + (size_t)i * M + col;
                     if (saveT) saveT[o] = T[j];
-                    if (saveW) saveW[o] = W[j];
+                    if (SAVEW) saveW[o] = W[j];
                 }
             }
         }
@@ -273,11 +275,11 @@ __global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__
 
 } // namespace cgb
 
-template <int CPL, int MODE, int MINB>
+template <int CPL, int MODE, int MINB, bool SAVEW>
 static int lite_warp_launch_b(cgb_handle* h, const cgb::FastTargets& tg, double* saveT, double* saveW)
 {
     using namespace cgb;
-    auto kern = k_lite_warp<CPL, MODE, MINB>;
+    auto kern = k_lite_warp<CPL, MODE, MINB, SAVEW>;
     size_t smem = (size_t)(5 * CPL * 32 + 4 * h->nl * LC_STRIDE + 4 * 16) * sizeof(double);
     int blocks_per_sm = 0;
     CUDA_TRY(h, cgb_prepare_kernel(h, (const void*)kern, smem, &blocks_per_sm));
@@ -293,7 +295,7 @@ static int lite_warp_launch_b(cgb_handle* h, const cgb::FastTargets& tg, double*
 template <int CPL, int MODE>
 static int lite_warp_launch_m(cgb_handle* h, const cgb::FastTargets& tg, double* saveT, double* saveW)
 {
-    return lite_warp_launch_b<CPL, MODE, 2>(h, tg, saveT, saveW);
+    return saveW ? lite_warp_launch_b<CPL, MODE, 2, true>(h, tg, saveT, saveW) : lite_warp_launch_b<CPL, MODE, 2, false>(h, tg, saveT, saveW);
 }
 
 template <int CPL>
