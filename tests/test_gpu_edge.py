@@ -140,3 +140,37 @@ def test_heterogeneous_per_cell_parameters(orc):
                 Hr, *_ = oc.lite_advance(H0[:, c], 0.0, 86400.0, tt)
             np.testing.assert_allclose(H[:, c], Hr, rtol=1e-9, atol=1e-2)
         eng.close()
+
+
+@pytest.mark.parametrize("n", [2, 31, 33, 65, 100, 225, 290, 385, 512])
+@pytest.mark.parametrize("kind", ["newton", "lut", "mixed"])
+def test_sfcc_all_grid_sizes(orc, n, kind):
+    # every cells-per-lane instantiation of the general stepping kernel: SFCC + Newton (interleaved cell->lane mapping),
+    # SFCC + presolver LUT (contiguous mapping) and a FreeWater / SFCC-Newton stratigraphy (generic mode, interleaved)
+    M = 3
+    grid = _grid(n)
+    fc = cg.DallAmico(swrc=cg.VanGenuchten(alpha=1.5, n=1.7))
+    top_soil = cg.SimpleSoil(por=0.55, sat=1.0, org=0.1, freezecurve=fc) if kind != "mixed" else cg.SimpleSoil(por=0.55, org=0.1)
+    deep_soil = cg.SimpleSoil(por=0.35, sat=1.0, org=0.0, freezecurve=cg.PainterKarra(swrc=cg.VanGenuchten(alpha=0.8, n=2.2)))
+    zmid = grid.edges[max(1, n // 3)]
+    prof = [(0.0, top_soil)] + ([(zmid, deep_soil)] if n >= 3 else [])
+    fcsolver = cg.SFCCPreSolver() if kind == "lut" else cg.SFCCNewtonSolver()
+    tile = cg.SoilHeatTile("H", cg.PeriodicBC(cg.Dirichlet, 86400.0 * 20, 9.0, 0.0, -1.0), cg.GeothermalHeatFlux(0.05), cg.SoilProfile(*prof), None,
+                           cg.initializer("T", cg.TemperatureProfile((0.0, -3.0), (grid.edges[-1], 1.0))), grid=grid, fcsolver=fcsolver, ncolumns=M)
+    H0 = cg.initialcondition(tile)
+    eng = cg.Engine(tile, dtmax=30.0, dtmin=0.5)
+    eng.set_state(H0, 0.0)
+    dH = eng.rhs(100.0)
+    tt = 1800.0
+    eng.advance_to(tt)
+    H, t, dt = eng.get_state(with_time=True)
+    st, steps = eng.status()
+    assert not st.any() and np.all(t == tt)
+    for c in (0, M - 1):
+        oc = orc.OracleColumn(tile, c)
+        dref, _ = oc.rhs(H0[:, c], 100.0)
+        assert common.rhs_error(dH[:, c], dref, oc.work.get("jH"), tile.grid.dedges) < 1e-10
+        Hr, tr, dtr, ns, s2 = oc.advance(H0[:, c], 0.0, 60.0, tt, dtmin=0.5, dtmax=30.0)
+        assert steps[c] == ns
+        np.testing.assert_allclose(H[:, c], Hr, rtol=1e-9, atol=1e-2)
+    eng.close()
