@@ -175,3 +175,18 @@ def test_multi_target_saveat_equals_single_launches(solver):
         np.testing.assert_allclose(a.get_state(), b.get_state(), rtol=1e-9, atol=1.0)
     assert a.stats()["kernel_launches"] < b.stats()["kernel_launches"]
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("solver", ["lut", "newton"])
+def test_advance_sfcc_one_year(orc, solver):
+    # the north_star gate on SFCC columns: <= 1e-6 K and <= 1e-8 θw against the oracle after ONE simulated year (a full
+    # freeze-thaw cycle: every cell of the active layer crosses the kink of its freeze curve twice), equal step counts.
+    # dtmax = 900 s is below the diffusion limit of the 10 cm cells (DESIGN.md "sensitivity finding").
+    tile = common.sfcc_tile(ncolumns=2, kind="dallamico", solver=solver, alpha=2.0, n=1.6, grid=cg.DefaultGrid_10cm,
+                            top=cg.PeriodicBC(cg.Dirichlet, common.YEAR, 15.0, 0.0, -4.0), bottom=cg.GeothermalHeatFlux(0.053),
+                            temp=cg.TemperatureProfile((0.0, -4.0), (20.0, -3.0), (1000.0, 12.0)))
+    H0 = cg.initialcondition(tile)
+    eng = cg.Engine(tile, dtmax=900.0)
+    worst = _check_advance(orc, tile, eng, H0, 0.0, [86400.0 * d for d in (120, 240, 365)], dtmax=900.0, cols=[0])
+    print(f"one year SFCC ({solver}): max |dT| {worst['T']:.2e} K, max |dθw| {worst['thw']:.2e}")
+    eng.close()
