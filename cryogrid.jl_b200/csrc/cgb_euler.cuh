@@ -260,16 +260,18 @@ __device__ __forceinline__ void stage_a_lut(const Dev& P, const double* lcw, con
             if (DERIV) q[j] = (lcw + loff[j])[LC_ALPHA] * x[j] * (rs * rs * rs);
         }
     } else {
+        // the powers of all cells in one straight-line block: with exp_fast / log_pos (~150 instructions per cell) the CPL
+        // copies fit the instruction cache and their dependency chains interleave (+8 % over an out-of-line call per cell)
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
             const double* lc = lcw + loff[j];
             double n = lc[LC_N], m = lc[LC_M];
-            pb[j] = 1.0; q[j] = 0.0;
-            if (x[j] > 0.0) {                         // skipped by the whole warp for thawed, saturated cells
-                double2 r = vg_powers(x[j], n, m);
-                pb[j] = r.y;
-                if (DERIV) q[j] = m * n * lc[LC_ALPHA] * (r.x * rcp_fast(x[j])) * (r.y * rcp_fast(1.0 + r.x));
-            }
+            double xs = sel_max(x[j], 1e-300);
+            double xn, p;
+            vg_powers_body(xs, n, m, xn, p);
+            bool pos = x[j] > 0.0;
+            pb[j] = pos ? p : 1.0;
+            if (DERIV) q[j] = pos ? m * n * lc[LC_ALPHA] * (xn * rcp_fast(xs)) * (p * rcp_fast(1.0 + xn)) : 0.0;
         }
     }
 #pragma unroll
