@@ -101,10 +101,21 @@ def make_tile(columns, total_days, seed):
     return common.samoylov_freew_tile(ncolumns=columns, seed=seed, forcing_days=int(total_days) + 3)
 
 
+def host_threads():
+    """Host cores this process may use.  Not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its workers, which
+    would silently turn the CPU legs (all host threads, by contract) into single-thread runs."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_leg(tile, H0, seconds, nthreads=0, days=None):
     """Oracle restatement (OpenMP over columns) on a bounded column sample; returns (cell_steps/s, dict)."""
     import oracle as orc
-    cores = orc.lib().cg_max_threads() if nthreads == 0 else nthreads
+    if nthreads == 0:
+        nthreads = host_threads()
+    cores = nthreads
     ncol = min(tile.M, max(cores, 1) * 2)
     cols = np.arange(ncol)
     prepared = orc.batch_columns(tile, cols)
@@ -130,7 +141,7 @@ def run_reference(args):
         return
     import cryogrid_jl_b200 as cg
     import oracle as orc
-    cores = orc.lib().cg_max_threads()
+    cores = host_threads()
     ncol = max(cores, 1) * 2
     tile = make_tile(ncol, 400, seed=1)
     H0 = cg.initialcondition(tile)
@@ -140,19 +151,19 @@ def run_reference(args):
     H = np.ascontiguousarray(H0.T); t = np.zeros(ncol); dt = np.full(ncol, 60.0)
     # calibrate the per-step sample so that the whole run stays within ~2 minutes
     t0 = time.perf_counter()
-    orc.cgeuler_advance_batch(tile, cols, H, t, dt, 1.0 * DAY, prepared=prepared)
+    orc.cgeuler_advance_batch(tile, cols, H, t, dt, 1.0 * DAY, nthreads=cores, prepared=prepared)
     per_day = time.perf_counter() - t0
     budget = 100.0 / max(args.steps + args.warmup, 1)
     days = max(1.0, min(args.days_per_step, budget / max(per_day, 1e-4)))
     cur = 1.0
     for _ in range(args.warmup):
         cur += days
-        orc.cgeuler_advance_batch(tile, cols, H, t, dt, cur * DAY, prepared=prepared)
+        orc.cgeuler_advance_batch(tile, cols, H, t, dt, cur * DAY, nthreads=cores, prepared=prepared)
     cs = 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cur += days
-        st, ns = orc.cgeuler_advance_batch(tile, cols, H, t, dt, cur * DAY, prepared=prepared)
+        st, ns = orc.cgeuler_advance_batch(tile, cols, H, t, dt, cur * DAY, nthreads=cores, prepared=prepared)
         cs += int(ns.sum()) * N
     el = time.perf_counter() - t0
     val = cs / el
