@@ -3,10 +3,17 @@
 #include "cgb_euler_fast.cuh"
 using namespace cgb;
 
-// Tuned on B200 (profiles/): 3 resident CTAs per SM (168 registers, no spills) and the cubic reciprocal
-// were the fastest of MINB in {2,3,4} x {two Newton steps, one cubic step}.
-constexpr int kFastMinB = 3;
-constexpr bool kFastCubic = true;
+// Tuned on B200 (profiles/): 3 resident CTAs per SM (168 registers) and the cubic reciprocal.  Re-measured with the
+// x3-unrolled step loop (cell-steps/s on cfg2): MINB 3 + cubic 3.62e11, MINB 3 + two Newton steps 3.47e11, MINB 2 (230 registers)
+// 3.54e11, MINB 4 (128 registers, 224 B spills) 3.53e11.  The macros exist for such A/B builds (build.py: CGB_NVCC_EXTRA).
+#ifndef CGB_FAST_MINB
+#define CGB_FAST_MINB 3
+#endif
+#ifndef CGB_FAST_CUBIC
+#define CGB_FAST_CUBIC true
+#endif
+constexpr int kFastMinB = CGB_FAST_MINB;
+constexpr bool kFastCubic = CGB_FAST_CUBIC;
 
 template <int CPL, bool SAVE>
 static int launch_fast_s(cgb_handle* h, const FastTargets& tg, double* saveT, double* saveW)
