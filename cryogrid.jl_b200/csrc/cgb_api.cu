@@ -594,7 +594,7 @@ static bool lite_thread_variant()
     return v && std::strcmp(v, "thread") == 0;
 }
 
-// solver mode of the general explicit kernel: 1 = every layer SFCC + LUT, 2 = every layer SFCC + Newton,
+// solver mode of the general explicit kernel: 1 = every layer SFCC + LUT (4: and every n == 2), 2 = every layer SFCC + Newton,
 // 3 = every layer FreeWater, 0 = mixed
 static int euler_mode(const cgb_handle* h)
 {
@@ -604,7 +604,15 @@ static int euler_mode(const cgb_handle* h)
         all_lut &= sf && h->fc_solver[l] == CGB_SOLVER_LUT;
         all_newton &= sf && h->fc_solver[l] == CGB_SOLVER_NEWTON;
     }
-    return all_lut ? 1 : all_newton ? 2 : all_freewater(h) ? 3 : 0;
+    if (all_lut) {
+        // mode 4: every van Genuchten n is exactly 2 (the value of the reference's SFCC example): rsqrt closed form
+        bool n2 = true;
+        auto it = h->params.find("vg_n");
+        if (it == h->params.end() || it->second.v.empty()) n2 = false;
+        else for (double v : it->second.v) n2 = n2 && (v == 2.0);
+        return n2 ? 4 : 1;
+    }
+    return all_newton ? 2 : all_freewater(h) ? 3 : 0;
 }
 
 // the stepping kernels that carry a column through several save times per launch (device-side saveat)

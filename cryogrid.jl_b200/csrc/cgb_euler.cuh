@@ -84,14 +84,6 @@ __device__ __forceinline__ void stage_layer_consts(const Dev& P, long long col, 
     for (int l = lane; l < P.n_layers; l += 32) layer_consts(P, col, l, lc + l * LC_STRIDE);
 }
 
-// true when every layer of the staged column has van Genuchten n == 2 (the rsqrt shortcut of stage_a_lut applies)
-__device__ __forceinline__ bool all_layers_n2(const Dev& P, const double* lcw, int lane)
-{
-    bool ok = true;
-    for (int l = lane; l < P.n_layers; l += 32) ok = ok && (lcw[l * LC_STRIDE + LC_N] == 2.0);
-    return __all_sync(FULL, ok);
-}
-
 // The freeze curve has a kink at T* (ψ stops depending on T above it), where dH/dT jumps by orders of magnitude; a Newton
 // iteration started on the wrong side needs many bracketing steps, and in a warp every lane waits for the one cell at the
 // freezing front.  So the side is decided first, exactly: H >= H(T*) is the thawed branch, which is LINEAR in T (closed
@@ -153,13 +145,13 @@ __device__ __forceinline__ double lut_T(const Dev& P, const double* lc, double H
 }
 
 // H -> (T, θw, C, dHdT, dθw/dT, kc) for one cell.
-// MODE: 0 = freeze curve / solver read from the layer constants (generic), 1 = every layer is SFCC + presolver LUT,
+// MODE: 0 = freeze curve / solver read from the layer constants (generic), 1 = every layer is SFCC + presolver LUT (4: and n == 2),
 //       2 = every layer is SFCC + Newton, 3 = every layer is FreeWater.  EXACT: fully converged Newton (diagnostics).
 template <int MODE, bool EXACT>
 __device__ __forceinline__ void freezethaw_body(const Dev& P, const double* lc, double H, double dC, double dK,
                                                 double& T, double& thw, double& C, double& dHdT, double& dth, double& kc)
 {
-    int kind = (MODE == 0) ? reinterpret_cast<const int*>(lc + LC_KIND)[0] : (MODE == 3 ? 0 : (MODE == 1 ? 1 : (1 | (1 << 8))));
+    int kind = (MODE == 0) ? reinterpret_cast<const int*>(lc + LC_KIND)[0] : (MODE == 3 ? 0 : ((MODE == 1 || MODE == 4) ? 1 : (1 | (1 << 8))));
     if ((kind & 0xff) == 0) {
         // FreeWater: heat_conduction.jl:18-57 (θw = clamp(H/Lθ,0,1) θtot; T piecewise; ∂H∂T = 1e8 at T == 0)
         double x = H * lc[LC_INVLTHTOT];
@@ -208,11 +200,12 @@ __device__ __forceinline__ void freezethaw_cell(const Dev& P, const double* lc, 
 // (3) T from the segment, (4) matric potential, (5) the van Genuchten powers of all cells in one block (exp/log chains
 // of different cells interleave; warp-uniform rsqrt shortcut when every n == 2), (6) C, dH/dT, kc.
 // Same arithmetic as freezethaw_body<1, .>.
-// DERIV = false skips dθw/dT, C and dH/dT (only the CFL limiter and the diagnostics kernel need them).
-template <int CPL, bool DERIV = true>
+// DERIV = false skips dθw/dT, C and dH/dT (only the CFL limiter and the diagnostics kernel need them).  N2 = every van
+// Genuchten n of the problem is 2 (decided on the host): the rsqrt shortcut, and no exp/log code in the kernel at all.
+template <int CPL, bool DERIV, bool N2>
 __device__ __forceinline__ void stage_a_lut(const Dev& P, const double* lcw, const int (&loff)[CPL], const double (&H)[CPL],
                                             double (&T)[CPL], double (&thw)[CPL], double (&C)[CPL], double (&dHdT)[CPL],
-                                            double (&dth)[CPL], double (&kc)[CPL], double dC, double dK, bool n2)
+                                            double (&dth)[CPL], double (&kc)[CPL], double dC, double dK)
 {
     int lo[CPL], hi[CPL];
     double Hq[CPL];
@@ -252,7 +245,7 @@ __device__ __forceinline__ void stage_a_lut(const Dev& P, const double* lcw, con
         if (DERIV) dpsi[j] = frozen ? lc[LC_CFAC] : 0.0;
         x[j] = (psi <= 0.0) ? fabs(-lc[LC_ALPHA] * psi) : -1.0;      // -1 marks ψ > 0 (θw = θsat)
     }
-    if (n2) {
+    if (N2) {
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
             double rs = rsqrt_fast(fma(x[j], x[j], 1.0));

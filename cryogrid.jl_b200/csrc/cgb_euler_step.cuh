@@ -18,12 +18,12 @@ struct StageA {
     // H -> T, θw, kc for the CPL cells of a lane, plus dH/dT where it is used (MODE 0/2: Newton predictor; deriv: CFL limiter)
     static __device__ __forceinline__ void run(const Dev& P, const double* lcw, const int (&loff)[CPL], const double (&H)[CPL],
                                                double (&T)[CPL], double (&thw)[CPL], double (&kc)[CPL], double (&dHdT)[CPL],
-                                               double dC, double dK, bool n2, bool deriv)
+                                               double dC, double dK, bool deriv)
     {
-        if (MODE == 1) {
+        if (MODE == 1 || MODE == 4) {
             double C[CPL], dth[CPL];
-            if (deriv) stage_a_lut<CPL, true>(P, lcw, loff, H, T, thw, C, dHdT, dth, kc, dC, dK, n2);
-            else stage_a_lut<CPL, false>(P, lcw, loff, H, T, thw, C, dHdT, dth, kc, dC, dK, n2);
+            if (deriv) stage_a_lut<CPL, true, MODE == 4>(P, lcw, loff, H, T, thw, C, dHdT, dth, kc, dC, dK);
+            else stage_a_lut<CPL, false, MODE == 4>(P, lcw, loff, H, T, thw, C, dHdT, dth, kc, dC, dK);
         } else {
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
@@ -98,7 +98,6 @@ __global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, const
         __syncwarp();
         stage_layer_consts(P, col, lcw, lane);
         __syncwarp();
-        const bool n2 = (MODE == 1) && all_layers_n2(P, lcw, lane);
 
         double H[CPL], T[CPL], thw[CPL], kc[CPL], dHdT[CPL];
 #pragma unroll
@@ -128,7 +127,7 @@ __global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, const
         const double t_target = TG.t[kt];
         if (t < t_target) {
             boundary(t);
-            StageA<CPL, MODE>::run(P, lcw, loff, H, T, thw, kc, dHdT, dC, dK, n2, cfl);
+            StageA<CPL, MODE>::run(P, lcw, loff, H, T, thw, kc, dHdT, dC, dK, cfl);
         }
 
         while (t < t_target && !(status & 4)) {
@@ -219,7 +218,7 @@ __global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, const
             // ... and overlap them with the next step's boundary values and diagnostics
             if (tn < t_target) {
                 boundary(tn);
-                StageA<CPL, MODE>::run(P, lcw, loff, H, T, thw, kc, dHdT, dC, dK, n2, cfl);
+                StageA<CPL, MODE>::run(P, lcw, loff, H, T, thw, kc, dHdT, dC, dK, cfl);
             }
             // ---- next dt: timestep() from the OLD du (basic_solvers.jl:76-77, steplimiters.jl:15-18), then the saveat! clip
             maxabs = __hiloint2double((int)rh, (int)rl);
