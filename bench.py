@@ -59,41 +59,59 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region: one streaming `nvidia-smi -lms 100` process
+    (started early, so its start-up latency is not part of the window), time-stamped rows, and a window set by
+    mark_start()/mark_end().  Rows outside the window (warm-up under the same load) are the fallback if none fell inside."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
         self.th = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop.is_set():
-            try:
-                r = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5)
-                if r.returncode == 0 and r.stdout.strip():
-                    self.rows.append([x.strip() for x in r.stdout.strip().split(",")])
-            except Exception:
-                pass
-            self.stop.wait(0.2)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                r = [x.strip() for x in line.strip().split(",")]
+                if len(r) >= 6:
+                    self.rows.append((time.perf_counter(), r))
+        except Exception:
+            pass
 
     def __enter__(self):
         self.th.start()
         return self
 
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
     def __exit__(self, *a):
-        self.stop.set()
+        if self.t1 is None:
+            self.mark_end()
+        time.sleep(0.15)                       # let the sample that covers the end of the window arrive
+        if self.proc is not None:
+            self.proc.terminate()
         self.th.join(timeout=6)
 
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        t0 = self.t0 if self.t0 is not None else -1.0
+        t1 = self.t1 if self.t1 is not None else float("inf")
+        inside = [r for t, r in self.rows if t0 <= t <= t1 + 0.1]
+        rows = inside or [r for _, r in self.rows]
+        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows if len(r) > 2 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(rows[0][1]) if rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(rows), "samples_in_timed_region": len(inside)}
 
 
 def make_tile(columns, total_days, seed):
@@ -208,15 +226,16 @@ def main():
     H0 = cg.initialcondition(tile)
     eng = cg.Engine(tile, stepper="euler", device=local)
     eng.set_state(H0, 0.0)
-    for w in range(W):
-        eng.advance_to((w + 1) * D * DAY)
-    eng.synchronize()
-    s0 = eng.stats()
-    eng.profile_enable(True)
-    eng.profile_read()
-    barrier()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")     # > 126 MB L2
-    with ClockSampler(local) as clk:
+    with ClockSampler(local) as clk:           # streaming sampler: started before the warm-up, windowed to the timed region
+        for w in range(W):
+            eng.advance_to((w + 1) * D * DAY)
+        eng.synchronize()
+        s0 = eng.stats()
+        eng.profile_enable(True)
+        eng.profile_read()
+        barrier()
+        clk.mark_start()
         t_wall = time.perf_counter()
         for k in range(K):
             flush.zero_()                      # L2 flush between timed steps (outside the CUDA-event brackets of the kernels)
@@ -224,6 +243,7 @@ def main():
             eng.advance_to((W + k + 1) * D * DAY, sync=True)
         barrier()
         wall = time.perf_counter() - t_wall
+        clk.mark_end()
     n_launch, kern_ms = eng.profile_read()
     eng.profile_enable(False)
     s1 = eng.stats()
