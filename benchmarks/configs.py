@@ -61,6 +61,14 @@ def main():
         return only is None or name in only or name[:4] in only      # cfg4 selects cfg4a, cfg4b, cfg4c
 
     if want("cfg1"):
+        # cfg1a: examples/heat_sfcc_constantbc.jl AS WRITTEN -- the script defines an SFCC but SimpleSoil() keeps its default
+        # FreeWater (oddity 1): one FreeWater column, constant 10 W/m² in/out, dtmax = 900 s, 30 days
+        tile = cg.SoilHeatTile("H", cg.ConstantBC(cg.Neumann, 10.0), cg.ConstantBC(cg.Neumann, 10.0), cg.SoilProfile((0.0, cg.SimpleSoil())), None,
+                               cg.initializer("T", cg.TemperatureProfile((0.0, -20.0), (1000.0, 10.0))), grid=cg.DefaultGrid_10cm, ncolumns=1)
+        H0 = cg.initialcondition(tile)
+        eng = cg.Engine(tile, dtmax=900.0); eng.set_state(H0, 0.0); eng.advance_to(DAY)
+        r = timed(eng, [DAY * d for d in range(2, 32)]); r.update(config="cfg1a single FreeWater column (example as written), N=178, 30 days", columns=1)
+        out.append(r); eng.close()
         # cfg1b: single SFCC column (PainterKarra α=1, n=2), constant 10 W/m² in/out, dtmax=900 s, 30 days
         tile = common.sfcc_tile(ncolumns=1, kind="painterkarra", solver="lut")
         H0 = cg.initialcondition(tile)
