@@ -19,3 +19,5 @@ from .solvers import CGEuler, LiteImplicitEuler, CryoGridProblem, CryoGridSoluti
 
 SamoylovDefault_tempprofile = TemperatureProfile(   # models.jl:35-44
     (0.0, -1.0), (0.2, -1.0), (2.0, -1.0), (5.0, -3.0), (9.5, -6.0), (25.0, -9.0), (100.0, -9.0), (1000.0, 10.2))
+
+from . import presets  # noqa: E402  (needs the names above)

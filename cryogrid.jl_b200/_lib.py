@@ -65,6 +65,7 @@ SIGNATURES = {
     "cgb_set_forcing_periodic": (C.c_int, [_P, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double]),
     "cgb_set_forcing_constant": (C.c_int, [_P, C.c_int32, C.c_double]),
     "cgb_set_state": (C.c_int, [_P, _D, C.c_double]),
+    "cgb_restore_state": (C.c_int, [_P, _D, _D, _D, _I64]),
     "cgb_init_interp": (C.c_int, [_P, _D, _D, C.c_int64, C.c_int32, C.c_double]),
     "cgb_init_steadystate": (C.c_int, [_P, _D, C.c_int32, C.c_double, C.c_int32, C.c_double, C.c_double]),
     "cgb_get_state": (C.c_int, [_P, _D, _D, _D]),

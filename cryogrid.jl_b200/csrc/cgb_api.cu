@@ -416,6 +416,30 @@ extern "C" int cgb_set_state(cgb_handle* h, const double* u, double t0)
     return CGB_OK;
 }
 
+extern "C" int cgb_restore_state(cgb_handle* h, const double* u, const double* t, const double* dt, const int64_t* steps)
+{
+    clear_stale_error("cgb_restore_state");
+    if (!h || !u || !t || !dt) return CGB_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const size_t M = (size_t)h->M, nu = (size_t)h->nvar * h->N * M;
+    double tmax = t[0];
+    for (size_t c = 0; c < M; ++c) {
+        if (!(dt[c] > 0.0) || !std::isfinite(t[c])) CGB_FAIL(h, CGB_ERR_INVALID, "cgb_restore_state: column %zu has t = %g, dt = %g", c, t[c], dt[c]);
+        tmax = std::max(tmax, t[c]);
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(h->dev.u, u, nu * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->dev.t, t, M * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->dev.dt, dt, M * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (steps) CUDA_TRY(h, cudaMemcpyAsync(h->dev.steps, steps, M * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    else CUDA_TRY(h, cudaMemsetAsync(h->dev.steps, 0, M * sizeof(long long), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->dev.iters, 0, M * sizeof(long long), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->dev.status, 0, M * sizeof(int), h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->have_state = true;
+    h->t_front = tmax;
+    return CGB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // on-device initial conditions
 // ------------------------------------------------------------------------------------------------

@@ -33,6 +33,16 @@ class _EngineBase:
         self._check(self.lib.cgb_get_stats(self.h, C.byref(s)))
         return {f[0]: getattr(s, f[0]) for f in L.Stats._fields_ if f[0] != "_pad"}
 
+    def restore_state(self, u, t, dt, steps=None):
+        """Checkpoint restore (counterpart of get_state(with_time=True)): per-column time and next step size."""
+        u = L.as_f64(u)
+        if u.size != getattr(self, "nvar", 1) * self.N * self.M:
+            raise ValueError(f"state has {u.size} elements, expected {getattr(self, 'nvar', 1) * self.N * self.M}")
+        t = L.as_f64(np.broadcast_to(t, (self.M,))); dt = L.as_f64(np.broadcast_to(dt, (self.M,)))
+        st = None if steps is None else np.ascontiguousarray(steps, dtype=np.int64)
+        self._check(self.lib.cgb_restore_state(self.h, L.dptr(u), L.dptr(t), L.dptr(dt),
+                                               None if st is None else st.ctypes.data_as(C.POINTER(C.c_int64))))
+
     def advance_to(self, t_target, sync=True):
         self._check(self.lib.cgb_advance_to(self.h, float(t_target)))
         if sync:

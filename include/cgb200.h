@@ -159,6 +159,11 @@ int cgb_init_interp(cgb_handle* h, const double* zk, const double* vk, int64_t n
 int cgb_init_steadystate(cgb_handle* h, const double* T0, int32_t per, double Qgeo, int32_t maxiters, double thresh, double t0);
 /* u, and optionally per-column t and dt (either may be NULL). This is also the checkpoint. */
 int cgb_get_state(cgb_handle* h, double* u, double* t, double* dt);
+/* Checkpoint restore: the counterpart of cgb_get_state.  u as in cgb_set_state, t[M] and dt[M] the per-column time and NEXT
+ * step size a checkpoint returned (integrator.t / integrator.dt, Solvers/integrator.jl:40-52); steps[M] may be NULL (counters
+ * restart at 0).  Status words are cleared.  A run continued from a checkpoint takes exactly the steps the uninterrupted run
+ * takes (tests/test_restart_parity.py). */
+int cgb_restore_state(cgb_handle* h, const double* u, const double* t, const double* dt, const int64_t* steps);
 /* per-column status words / step counts (M entries each, either may be NULL) */
 int cgb_get_status(cgb_handle* h, int32_t* status, int64_t* steps);
 int cgb_get_stats(cgb_handle* h, cgb_stats* out);

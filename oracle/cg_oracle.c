@@ -506,24 +506,42 @@ double cg_timestep(const cg_column* col, const double* H, const cg_work* w)
  * Advance one column from (*t,*dt) until t >= t_target; dt is clipped so the target is hit
  * exactly (saveat!), but -- as in the reference -- only after a step, never before the first.
  * ---------------------------------------------------------------------------------------- */
-int cg_cgeuler_advance(const cg_column* col, double* H, double* t, double* dt, double t_target,
-                       double dtmin, double dtmax, int64_t* nsteps, cg_work* w)
+/* Trace variant (test infrastructure for the restart-parity tests): dt_trace[k] = the dt step k was taken with
+ * (k < cap; may be NULL), *nlimited = number of steps whose NEXT dt was decided by the limiter itself, i.e.
+ * dtmin < lim < dtmax and not clipped by the save time. */
+int cg_cgeuler_advance_trace(const cg_column* col, double* H, double* t, double* dt, double t_target,
+                             double dtmin, double dtmax, int64_t* nsteps, cg_work* w,
+                             double* dt_trace, int64_t cap, int64_t* nlimited)
 {
     int status = 0;
     int n = col->n;
+    int64_t k = 0;
     while (*t < t_target) {
         status |= cg_rhs(col, H, *t, w);                  /* tile(du,u,p,t0) */
         for (int i = 0; i < n; ++i) H[i] += (*dt) * w->dH[i]; /* u += dt*du */
+        if (dt_trace && k < cap) dt_trace[k] = *dt;
+        ++k;
         *t = *t + *dt;
         if (nsteps) ++*nsteps;
         double lim = cg_timestep(col, H, w);              /* timestep from the old du */
         if (!(lim > 0.0)) status |= CG_STATUS_BAD_DT;     /* tile.jl:174 */
         *dt = fmax(fmin(lim, dtmax), dtmin);              /* basic_solvers.jl:77 */
-        if (*t < t_target) *dt = fmin(*dt, t_target - *t); /* saveat!: integrator.jl:126-131 */
+        int limited = (lim > dtmin && lim < dtmax);
+        if (*t < t_target) {
+            if (t_target - *t < *dt) limited = 0;
+            *dt = fmin(*dt, t_target - *t);               /* saveat!: integrator.jl:126-131 */
+        }
         *dt = fmin(dtmax, *dt);                           /* integrator.jl:89 */
+        if (nlimited && limited) ++*nlimited;
         if (status & (CG_STATUS_FORCING_RANGE)) break;
     }
     return status;
+}
+
+int cg_cgeuler_advance(const cg_column* col, double* H, double* t, double* dt, double t_target,
+                       double dtmin, double dtmax, int64_t* nsteps, cg_work* w)
+{
+    return cg_cgeuler_advance_trace(col, H, t, dt, t_target, dtmin, dtmax, nsteps, w, NULL, 0, NULL);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -753,13 +771,16 @@ double cg_salt_timestep(const cg_salt_column* col, const cg_salt_work* w)
     return fmin(dts, dth);
 }
 
-int cg_salt_advance(const cg_salt_column* col, double* T, double* c, double* t, double* dt, double t_target,
-                    double dtmin, double dtmax, int64_t* nsteps, cg_salt_work* w)
+int cg_salt_advance_trace(const cg_salt_column* col, double* T, double* c, double* t, double* dt, double t_target,
+                          double dtmin, double dtmax, int64_t* nsteps, cg_salt_work* w, double* dt_trace, int64_t cap)
 {
     int status = 0, n = col->n;
+    int64_t k = 0;
     while (*t < t_target) {
         cg_salt_rhs(col, T, c, w);
         for (int i = 0; i < n; ++i) { T[i] += (*dt) * w->dT[i]; c[i] += (*dt) * w->dc[i]; }
+        if (dt_trace && k < cap) dt_trace[k] = *dt;
+        ++k;
         *t = *t + *dt;
         if (nsteps) ++*nsteps;
         double lim = cg_salt_timestep(col, w);
@@ -769,6 +790,12 @@ int cg_salt_advance(const cg_salt_column* col, double* T, double* c, double* t, 
         *dt = fmin(dtmax, *dt);
     }
     return status;
+}
+
+int cg_salt_advance(const cg_salt_column* col, double* T, double* c, double* t, double* dt, double t_target,
+                    double dtmin, double dtmax, int64_t* nsteps, cg_salt_work* w)
+{
+    return cg_salt_advance_trace(col, T, c, t, dt, t_target, dtmin, dtmax, nsteps, w, NULL, 0);
 }
 
 /* ------------------------------------------------------------------------------------------

@@ -158,6 +158,9 @@ double cg_timestep(const cg_column* col, const double* H, const cg_work* w);
 /* ---- steppers ---- */
 int cg_cgeuler_advance(const cg_column* col, double* H, double* t, double* dt, double t_target,
                        double dtmin, double dtmax, int64_t* nsteps, cg_work* w);
+int cg_cgeuler_advance_trace(const cg_column* col, double* H, double* t, double* dt, double t_target,
+                             double dtmin, double dtmax, int64_t* nsteps, cg_work* w,
+                             double* dt_trace, int64_t cap, int64_t* nlimited);
 int cg_lite_step(const cg_column* col, double* H, double* t, double dt, int miniters, int maxiters,
                  double tol, int64_t* iters, cg_work* w);
 int cg_lite_advance(const cg_column* col, double* H, double* t, double* dt, double t_target,
@@ -198,6 +201,9 @@ void   cg_salt_rhs(const cg_salt_column* col, const double* T, const double* c, 
 double cg_salt_timestep(const cg_salt_column* col, const cg_salt_work* w);
 int    cg_salt_advance(const cg_salt_column* col, double* T, double* c, double* t, double* dt, double t_target,
                        double dtmin, double dtmax, int64_t* nsteps, cg_salt_work* w);
+
+int    cg_salt_advance_trace(const cg_salt_column* col, double* T, double* c, double* t, double* dt, double t_target,
+                             double dtmin, double dtmax, int64_t* nsteps, cg_salt_work* w, double* dt_trace, int64_t cap);
 
 /* ---- batch drivers (OpenMP over columns) for the CPU baseline ---- */
 int  cg_cgeuler_advance_batch(const cg_column* cols, int64_t M, double* H /* [M][n] */, double* t, double* dt,

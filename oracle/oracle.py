@@ -99,6 +99,12 @@ def lib():
         l.cg_timestep.restype = C.c_double; l.cg_timestep.argtypes = [C.POINTER(Column), _D, C.POINTER(Work)]
         l.cg_cgeuler_advance.restype = C.c_int
         l.cg_cgeuler_advance.argtypes = [C.POINTER(Column), _D, _D, _D, C.c_double, C.c_double, C.c_double, _I64, C.POINTER(Work)]
+        l.cg_cgeuler_advance_trace.restype = C.c_int
+        l.cg_cgeuler_advance_trace.argtypes = [C.POINTER(Column), _D, _D, _D, C.c_double, C.c_double, C.c_double, _I64, C.POINTER(Work),
+                                               _D, C.c_int64, _I64]
+        l.cg_salt_advance_trace.restype = C.c_int
+        l.cg_salt_advance_trace.argtypes = [C.POINTER(SaltColumn), _D, _D, _D, _D, C.c_double, C.c_double, C.c_double, _I64,
+                                            C.POINTER(SaltWork), _D, C.c_int64]
         l.cg_lite_step.restype = C.c_int
         l.cg_lite_step.argtypes = [C.POINTER(Column), _D, _D, C.c_double, C.c_int, C.c_int, C.c_double, _I64, C.POINTER(Work)]
         l.cg_lite_advance.restype = C.c_int
@@ -231,6 +237,15 @@ class OracleColumn:
                                       ns.ctypes.data_as(_I64), C.byref(self.work.c))
         return H, tt[0], dd[0], int(ns[0]), st
 
+    def advance_trace(self, H, t, dt, t_target, dtmin=1.0, dtmax=3600.0, cap=1 << 20):
+        """Like advance, plus the dt every step was taken with and the number of steps whose next dt the limiter decided."""
+        H = f64(H).copy(); tt = np.array([t], dtype=np.float64); dd = np.array([dt], dtype=np.float64)
+        ns = np.zeros(1, dtype=np.int64); nl = np.zeros(1, dtype=np.int64)
+        tr = np.zeros(cap)
+        st = lib().cg_cgeuler_advance_trace(C.byref(self.col), dp(H), dp(tt), dp(dd), float(t_target), float(dtmin), float(dtmax),
+                                            ns.ctypes.data_as(_I64), C.byref(self.work.c), dp(tr), cap, nl.ctypes.data_as(_I64))
+        return H, tt[0], dd[0], int(ns[0]), st, tr[:min(int(ns[0]), cap)].copy(), int(nl[0])
+
     def lite_advance(self, H, t, dt, t_target, miniters=2, maxiters=1000, tol=1e-3):
         H = f64(H).copy(); tt = np.array([t], dtype=np.float64); dd = np.array([dt], dtype=np.float64)
         ns = np.zeros(1, dtype=np.int64); it = np.zeros(1, dtype=np.int64)
@@ -314,3 +329,11 @@ class OracleSaltColumn:
         st = lib().cg_salt_advance(C.byref(self.col), dp(T), dp(c), dp(tt), dp(dd), float(t_target), float(dtmin), float(dtmax),
                                    ns.ctypes.data_as(_I64), C.byref(self.w))
         return T, c, tt[0], dd[0], int(ns[0]), st
+
+    def advance_trace(self, T, c, t, dt, t_target, dtmin=1.0, dtmax=3600.0, cap=1 << 20):
+        T, c = f64(T).copy(), f64(c).copy()
+        tt = np.array([t], dtype=np.float64); dd = np.array([dt], dtype=np.float64); ns = np.zeros(1, dtype=np.int64)
+        tr = np.zeros(cap)
+        st = lib().cg_salt_advance_trace(C.byref(self.col), dp(T), dp(c), dp(tt), dp(dd), float(t_target), float(dtmin), float(dtmax),
+                                         ns.ctypes.data_as(_I64), C.byref(self.w), dp(tr), cap)
+        return T, c, tt[0], dd[0], int(ns[0]), st, tr[:min(int(ns[0]), cap)].copy()
