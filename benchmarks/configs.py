@@ -10,10 +10,9 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, "tests")):
-    sys.path.insert(0, p)
-import common  # noqa: E402
+sys.path.insert(0, ROOT)
 import cryogrid_jl_b200 as cg  # noqa: E402
+from cryogrid_jl_b200 import presets as common  # noqa: E402  (the synthetic BASELINE problem builders)
 
 DAY = 86400.0
 
@@ -99,43 +98,24 @@ def main():
         # the same steps with one launch per 5 days (a column stays in registers for 5 implicit steps)
         r = timed(eng, [DAY * d for d in range(375, 741, 5)]); r.update(config="cfg3 LiteImplicitEuler ensemble, N=278, 365 daily steps, 5 per launch", columns=M)
         out.append(r); eng.close()
-    rng = np.random.default_rng(4)
-    if want("cfg4a"):
+    for name, variant, label in (("cfg4a", "newton", "cfg4 SFCC DallAmico per-column parameters (Newton), N=218, 4 days"),
+                                 ("cfg4b", "lut", "cfg4' SFCC DallAmico presolver LUT (one soil class: SFCC fast path), N=218, 4 days"),
+                                 ("cfg4c", "lut_n2", "cfg4'' SFCC PainterKarra n=2 presolver LUT (one soil class: SFCC fast path), N=218, 4 days"),
+                                 ("cfg4d", "lut", "cfg4' through the GENERAL LUT kernel (CGB_SFCC_FAST=0), N=218, 4 days")):
+        if not want(name):
+            continue
         M = int(100000 * args.scale)
-        tile = common.sfcc_tile(ncolumns=M, kind="dallamico", solver="newton", per_column=True, grid=cg.DefaultGrid_5cm, seed=4,
-                                top=cg.PeriodicBC(cg.Dirichlet, common.YEAR, 18.0, 0.0, -10.0), bottom=cg.GeothermalHeatFlux(0.053),
-                                temp=cg.SamoylovDefault_tempprofile)
-        tile.top_offset = rng.normal(0.0, 2.0, M)
+        tile = common.cfg4_tile(M, variant)
         H0 = cg.initialcondition(tile)
+        if name == "cfg4d":
+            os.environ["CGB_SFCC_FAST"] = "0"
         eng = cg.Engine(tile); eng.set_state(H0, 0.0); eng.advance_to(1 * DAY)
-        r = timed(eng, [DAY * d for d in range(2, 6)]); r.update(config="cfg4 SFCC DallAmico per-column parameters (Newton), N=218, 4 days", columns=M)
-        out.append(r); eng.close()
-    if want("cfg4b"):
-        # same physics through the presolver LUT (one parameter class)
-        M = int(100000 * args.scale)
-        tile = common.sfcc_tile(ncolumns=M, kind="dallamico", solver="lut", alpha=2.0, n=1.6, grid=cg.DefaultGrid_5cm,
-                                top=cg.PeriodicBC(cg.Dirichlet, common.YEAR, 18.0, 0.0, -10.0), bottom=cg.GeothermalHeatFlux(0.053),
-                                temp=cg.SamoylovDefault_tempprofile)
-        tile.top_offset = rng.normal(0.0, 2.0, M)
-        H0 = cg.initialcondition(tile)
-        eng = cg.Engine(tile); eng.set_state(H0, 0.0); eng.advance_to(1 * DAY)
-        r = timed(eng, [DAY * d for d in range(2, 6)]); r.update(config="cfg4' SFCC DallAmico presolver LUT, N=218, 4 days", columns=M)
-        out.append(r); eng.close()
-    if want("cfg4c"):
-        # PainterKarra with van Genuchten n = 2 (the value examples/heat_sfcc_constantbc.jl uses): rsqrt fast path
-        M = int(100000 * args.scale)
-        tile = common.sfcc_tile(ncolumns=M, kind="painterkarra", solver="lut", alpha=1.0, n=2.0, grid=cg.DefaultGrid_5cm,
-                                top=cg.PeriodicBC(cg.Dirichlet, common.YEAR, 18.0, 0.0, -10.0), bottom=cg.GeothermalHeatFlux(0.053),
-                                temp=cg.SamoylovDefault_tempprofile)
-        tile.top_offset = rng.normal(0.0, 2.0, M)
-        H0 = cg.initialcondition(tile)
-        eng = cg.Engine(tile); eng.set_state(H0, 0.0); eng.advance_to(1 * DAY)
-        r = timed(eng, [DAY * d for d in range(2, 6)]); r.update(config="cfg4'' SFCC PainterKarra n=2 presolver LUT, N=218, 4 days", columns=M)
+        os.environ.pop("CGB_SFCC_FAST", None)
+        r = timed(eng, [DAY * d for d in range(2, 6)]); r.update(config=label, columns=M)
         out.append(r); eng.close()
     if want("cfg5"):
         M = int(100000 * args.scale)
-        rng = np.random.default_rng(5)
-        tile = cg.SalineTile(grid=cg.DefaultGrid_10cm, salt_bc=cg.SaltGradient(rng.uniform(600.0, 1000.0, M), 0), ncolumns=M)
+        tile = common.cfg5_tile(M)
         eng = cg.SaltEngine(tile); eng.set_state(tile.initialcondition(), 0.0); eng.advance_to(1 * DAY)
         r = timed(eng, [DAY * d for d in range(2, 6)]); r.update(config="cfg5 heat+salt, N=178, 4 days", columns=M)
         out.append(r); eng.close()

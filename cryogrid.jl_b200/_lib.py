@@ -83,6 +83,7 @@ SIGNATURES = {
     "cgb_profile_enable": (C.c_int, [_P, C.c_int32]),
     "cgb_profile_read": (C.c_int, [_P, _I64, C.POINTER(C.c_double)]),
     "cgb_selftest_rcp": (C.c_int, [_D, C.c_int64, _D, _D, _D]),
+    "cgb_selftest_sfcc_curve": (C.c_int, [_P, _D, C.c_int64, _D]),
     "cgb_selftest_explog": (C.c_int, [_D, C.c_int64, _D, _D]),
 }
 

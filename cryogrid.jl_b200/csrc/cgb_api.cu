@@ -385,6 +385,8 @@ static int finalize(cgb_handle* h)
     // heat+salt extras
     rc = cgb_salt_finalize(h, zc);
     if (rc) return rc;
+    rc = cgb_sfcc_fast_prepare(h);           // SFCC single-class fast path: eligibility + shared-memory tables
+    if (rc) return rc;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->dirty = false;
     return CGB_OK;
@@ -652,6 +654,7 @@ static int launch_multi(cgb_handle* h, const double* targets, int n, double* sav
 {
     if (h->cfg.stepper == CGB_STEPPER_LITE_IMPLICIT) return cgb_launch_lite_warp_multi(h, targets, n, saveT, saveW, save_stride);
     if (fast_path(h)) return cgb_launch_fast_multi(h, targets, n, saveT, saveW, save_stride);
+    if (h->sfcc_fast_ok) return cgb_launch_sfcc_fast_multi(h, targets, n, saveT, saveW, save_stride);
     Diag D{};
     D.T = saveT; D.thw = saveW;
     return cgb_launch_euler_step_multi(h, euler_mode(h), targets, n, D, save_stride);
@@ -1072,6 +1075,16 @@ extern "C" int cgb_selftest_rcp(const double* x, int64_t n, double* out_raw, dou
     cudaMemcpy(out_cubic, d + 3 * n, n * sizeof(double), cudaMemcpyDeviceToHost);
     cudaFree(d);
     return e == cudaSuccess ? CGB_OK : CGB_ERR_CUDA;
+}
+
+// self-test of the curve table of the SFCC single-class fast path: θw(T) as the stepping kernel evaluates it
+extern "C" int cgb_selftest_sfcc_curve(cgb_handle* h, const double* T, int64_t n, double* thw_out)
+{
+    if (!h || !T || !thw_out || n < 1) return CGB_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = finalize(h);
+    if (rc) return rc;
+    return cgb_sfcc_fast_selftest(h, T, (long long)n, thw_out);
 }
 
 // self-test of the transcendental replacements used by the van Genuchten powers (tests/test_gpu_sfcc.py)

@@ -105,6 +105,28 @@ struct Dev {
     int bot_layer_first;      // first cell of the bottom layer (heat_implicit.jl:83 quirk)
 };
 
+// ---- SFCC fast path (cgb_euler_sfcc_fast.cuh): tables of the unique soil class
+constexpr int SF_CURVE_STRIDE = 10;    // doubles per bin: 8 coefficients + 2 of padding (80 B rows: LDS.128 bank skew)
+constexpr int SF_SEG_STRIDE = 4;       // doubles per presolver segment: H_i, slope_i, T_i, pad
+
+// Everything the kernel needs about the (unique) soil class; passed by value -> constant bank.
+struct SfccFast {
+    // presolver interpolant
+    double hmin, invbw;        // bucket = (int)((H - hmin) * invbw), clamped to [0, nb-1]
+    double hlo, hhi;           // knot range (flat extrapolation clamps H to it)
+    int nk, nb, extrap_flat, nbins;
+    // freeze curve
+    double tstarK;             // T* [K]
+    double thw_thawed;         // θw for T >= T*  (= θ(ψ0))
+    int idx_base;              // (hi word >> 16) of the lower edge of bin 0
+    int _pad;
+    double fit_error;          // measured max relative error of the curve table against the closed form (host, long double)
+    double kb, dK;             // sqrt-sum conductivity at θw = 0, sk_w - sk_i (thermal_properties.jl:37)
+    // shared-memory blob (copied verbatim from `blob`): byte offsets, all multiples of 16
+    const double* blob;
+    int blob_bytes, off_seg, off_bucket, off_curve;
+};
+
 // heat+salt extras (Physics/Salt)
 struct SaltDev {
     const double* por_cell;   // [N] porosity profile (SedimentCompactionInitializer), shared by all columns

@@ -42,6 +42,9 @@ struct cgb_handle {
     bool have_state = false;
     double t_front = 0.0;     // latest time any advance was asked to reach (host-side bookkeeping for the save path)
     bool fast_ok = false;     // FreeWater fast kernel applicable (set by finalize)
+    bool sfcc_fast_ok = false; // SFCC single-class fast kernel applicable (set by finalize -> cgb_sfcc_fast_prepare)
+    cgb::SfccFast sf{};
+    int sf_threads = 384;
     // device memory
     std::vector<void*> allocs;
     size_t n_state_allocs = 0;   // allocations made by cgb_create (the rest belong to the description)

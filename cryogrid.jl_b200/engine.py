@@ -228,6 +228,12 @@ class Engine(_EngineBase):
             L.dptr(out) if cells.size else None, L.dptr(thaw_out) if thawdepth else None))
         return out, thaw_out
 
+    def selftest_sfcc_curve(self, T):
+        """θw(T) from the curve table of the SFCC single-class fast path (raises CgbError(UNSUPPORTED) if the tile does not qualify)."""
+        T = L.as_f64(T); out = np.empty_like(T)
+        self._check(self.lib.cgb_selftest_sfcc_curve(self.h, L.dptr(T), T.size, L.dptr(out)))
+        return out
+
     def ensemble_partial(self, var, t):
         s = np.empty(self.N); q = np.empty(self.N)
         self._check(self.lib.cgb_ensemble_partial(self.h, var.encode(), float(t), L.dptr(s), L.dptr(q)))

@@ -232,6 +232,12 @@ int cgb_selftest_rcp(const double* x, int64_t n, double* out_raw, double* out_ne
  * out_exp[i] = exp_fast(x[i]) (argument clamped to [-708, 709]), out_log[i] = log_pos(|x[i]|) (normal range). */
 int cgb_selftest_explog(const double* x, int64_t n, double* out_exp, double* out_log);
 
+/* Self-test of the SFCC single-class fast path (many columns of ONE soil class through the presolver LUT, MaxDelta limiter:
+ * csrc/cgb_euler_sfcc_fast.cuh): thw_out[i] = θw(T[i]) evaluated from the shared-memory curve table exactly as the stepping
+ * kernel does (degree-7 piecewise polynomials on log-spaced bins of T* - T, replacing the two pow() of the closed form that
+ * Soils/soil_heat.jl:131-139 evaluates after the table lookup).  CGB_ERR_UNSUPPORTED when the handle does not qualify. */
+int cgb_selftest_sfcc_curve(cgb_handle* h, const double* T, int64_t n, double* thw_out);
+
 #ifdef __cplusplus
 }
 #endif
