@@ -113,12 +113,11 @@ constexpr int SF_SEG_STRIDE = 4;       // doubles per presolver segment: H_i, sl
 struct SfccFast {
     // presolver interpolant
     double hmin, invbw;        // bucket = (int)((H - hmin) * invbw), clamped to [0, nb-1]
-    double hlo, hhi;           // knot range (flat extrapolation clamps H to it)
-    int nk, nb, extrap_flat, nbins;
+    int nk, nb, nbins, _pad0;
     // freeze curve
     double tstarK;             // T* [K]
-    double thw_thawed;         // θw for T >= T*  (= θ(ψ0))
-    int idx_base;              // (hi word >> 16) of the lower edge of bin 0
+    double thw_thawed;         // θw for T >= T*  (= θ(ψ0)); also row 0 of the curve table
+    int idx_base;              // (hi word >> 16) of the lower edge of curve row 1, minus 1 (row 0 = thawed constant)
     int _pad;
     double fit_error;          // measured max relative error of the curve table against the closed form (host, long double)
     double kb, dK;             // sqrt-sum conductivity at θw = 0, sk_w - sk_i (thermal_properties.jl:37)

@@ -129,31 +129,28 @@ __global__ void __launch_bounds__(THREADS, 1) k_heat_sfcc_fast(const __grid_cons
         double T[CPL], kc[CPL], thw[SAVE ? CPL : 1];
         auto stage_a = [&]() {
             int lo[CPL];
-            double Hq[CPL];
+            unsigned wd[CPL];
             unsigned trips = 0;
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
-                Hq[j] = S.extrap_flat ? sel_min(sel_max(H[j], S.hlo), S.hhi) : H[j];
-                int b = __double2int_rz((Hq[j] - S.hmin) * S.invbw);
-                b = min(max(b, 0), S.nb - 1);
-                unsigned w = sBucket[b];
-                lo[j] = (int)(w & 0xfffu);
-                trips = max(trips, w >> 12);
+                // bucket of H (flat extrapolation is part of the table: zero-slope end segments, see cgb_tu_sfcc_fast.cu); the
+                // unsigned conversion saturates negative arguments to 0
+                unsigned b = min(__double2uint_rz((H[j] - S.hmin) * S.invbw), (unsigned)(S.nb - 1));
+                wd[j] = sBucket[b];
+                lo[j] = (int)(wd[j] & 0xfffu);
+                trips = max(trips, wd[j]);
             }
-            if (__any_sync(FULL, trips != 0)) {
+            if (__any_sync(FULL, trips > 0xfffu)) {
                 // knots pile up only at the kink of the freeze curve: a bucket there holds up to 2^trips segments
-                const int nit = (int)__reduce_max_sync(FULL, trips);
+                const int nit = (int)(__reduce_max_sync(FULL, trips) >> 12);
                 int hi[CPL];
 #pragma unroll
-                for (int j = 0; j < CPL; ++j) {
-                    int b = min(max(__double2int_rz((Hq[j] - S.hmin) * S.invbw), 0), S.nb - 1);
-                    hi[j] = lo[j] + (1 << (sBucket[b] >> 12)) - 1;
-                }
+                for (int j = 0; j < CPL; ++j) hi[j] = lo[j] + (1 << (wd[j] >> 12)) - 1;
                 for (int k = 0; k < nit; ++k) {
 #pragma unroll
                     for (int j = 0; j < CPL; ++j) {
                         int mid = (lo[j] + hi[j] + 1) >> 1;
-                        bool p = sSeg[mid * SF_SEG_STRIDE] <= Hq[j];        // +Inf padded beyond the last knot
+                        bool p = sSeg[mid * SF_SEG_STRIDE] <= H[j];         // +Inf padded beyond the last knot
                         lo[j] = p ? mid : lo[j];
                         hi[j] = p ? hi[j] : mid - 1;
                     }
@@ -165,27 +162,28 @@ __global__ void __launch_bounds__(THREADS, 1) k_heat_sfcc_fast(const __grid_cons
             for (int j = 0; j < CPL; ++j) {
                 const double2 hs = *reinterpret_cast<const double2*>(sSeg + lo[j] * SF_SEG_STRIDE);      // H_i, slope_i
                 const double Ti = sSeg[lo[j] * SF_SEG_STRIDE + 2];
-                T[j] = fma(Hq[j] - hs.x, hs.y, Ti);
+                T[j] = fma(H[j] - hs.x, hs.y, Ti);
                 // u = T* - TK with the reference's rounding sequence (TK = T + 273.15 first)
                 const double u = S.tstarK - (T[j] + 273.15);
                 const int uh = __double2hiint(u), ul = __double2loint(u);
-                bin[j] = (uh >> 16) - S.idx_base;                          // < 0: u below the table (or negative): thawed
+                // row 0 of the curve table is the constant θw of the thawed branch: everything below the table (u tiny, zero or
+                // negative -- the sign bit makes the shifted word negative) lands there, without a select
+                bin[j] = min(max((uh >> 16) - S.idx_base, 0), S.nbins - 1);
                 const double m = __hiloint2double((uh & 0x000fffff) | 0x3ff00000, ul);
                 const double c = __hiloint2double(0x3ff08000 | (uh & 0x000f0000), 0);
-                r[j] = m - c;                                               // exact, |r| <= 1/32
+                r[j] = m - c;                                               // exact, |r| <= 1/32 (finite for any u)
             }
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
-                const double* cf = sCurve + min(max(bin[j], 0), S.nbins - 1) * SF_CURVE_STRIDE;
+                const double* cf = sCurve + bin[j] * SF_CURVE_STRIDE;
                 const double2 c01 = *reinterpret_cast<const double2*>(cf), c23 = *reinterpret_cast<const double2*>(cf + 2);
                 const double2 c45 = *reinterpret_cast<const double2*>(cf + 4), c67 = *reinterpret_cast<const double2*>(cf + 6);
                 double p = fma(c67.y, r[j], c67.x);
                 p = fma(p, r[j], c45.y); p = fma(p, r[j], c45.x);
                 p = fma(p, r[j], c23.y); p = fma(p, r[j], c23.x);
                 p = fma(p, r[j], c01.y); p = fma(p, r[j], c01.x);
-                const double w = (bin[j] < 0) ? S.thw_thawed : p;
-                if (SAVE) thw[j] = w;
-                const double sk = fma(S.dK, w, S.kb);
+                if (SAVE) thw[j] = p;
+                const double sk = fma(S.dK, p, S.kb);
                 kc[j] = sk * sk;
             }
         };
@@ -280,15 +278,15 @@ __global__ void k_selftest_sfcc_curve(const __grid_constant__ SfccFast S, const 
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const double u = S.tstarK - (Tin[i] + 273.15);
         const int uh = __double2hiint(u), ul = __double2loint(u);
-        const int bin = (uh >> 16) - S.idx_base;
+        const int bin = min(max((uh >> 16) - S.idx_base, 0), S.nbins - 1);
         const double m = __hiloint2double((uh & 0x000fffff) | 0x3ff00000, ul);
         const double c = __hiloint2double(0x3ff08000 | (uh & 0x000f0000), 0);
         const double r = m - c;
-        const double* cf = sCurve + min(max(bin, 0), S.nbins - 1) * SF_CURVE_STRIDE;
+        const double* cf = sCurve + bin * SF_CURVE_STRIDE;
         double p = cf[7];
 #pragma unroll
         for (int k = 6; k >= 0; --k) p = fma(p, r, cf[k]);
-        out[i] = (bin < 0) ? S.thw_thawed : p;
+        out[i] = p;
     }
 }
 

@@ -81,9 +81,14 @@ int cgb_sfcc_fast_prepare(cgb_handle* h)
     } else if (h->nl != 1) return CGB_OK;
     auto it = h->tables.find(table_id);
     if (it == h->tables.end()) return CGB_OK;
-    const std::vector<double>& Hk = it->second.H; const std::vector<double>& Tk = it->second.T;
-    const int nk = (int)Hk.size();
-    if (nk < 2 || nk > 4000) return CGB_OK;
+    if (it->second.H.size() < 2 || it->second.H.size() > 4000) return CGB_OK;
+    // Flat extrapolation (T = T_first below the first knot, T_last above the last) is built INTO the table: a sentinel knot far
+    // below the first one and a zero slope on both end records, so the kernel needs no clamp.  knot0 = index of the first real knot.
+    const bool flat = (it->second.extrap == CGB_EXTRAP_FLAT);
+    std::vector<double> Hk, Tk;
+    if (flat) { Hk.push_back(-1e300); Tk.push_back(it->second.T.front()); }
+    Hk.insert(Hk.end(), it->second.H.begin(), it->second.H.end()); Tk.insert(Tk.end(), it->second.T.begin(), it->second.T.end());
+    const int nk = (int)Hk.size(), knot0 = flat ? 1 : 0;
 
     auto G = [&](const char* n) { return h->params[n].v[0]; };
     const double por = G("por"), sat = G("sat"), org = G("org"), alpha = G("vg_alpha"), n = G("vg_n"), thres = G("theta_res");
@@ -117,8 +122,8 @@ int cgb_sfcc_fast_prepare(cgb_handle* h)
         Emin = E;
     }
     const int Emax = 9;                                   // bins cover [2^Emin, 2^(Emax+1))
-    S.nbins = (Emax + 1 - Emin) * 16;
-    S.idx_base = (Emin + 1023) << 4;
+    S.nbins = (Emax + 1 - Emin) * 16 + 1;                 // + row 0: the thawed constant
+    S.idx_base = ((Emin + 1023) << 4) - 1;
     // presolver buckets: as many as fit (power of two), same construction as the general path (cgb_api.cu finalize)
     const size_t seg_bytes = (size_t)(nk + 16) * SF_SEG_STRIDE * sizeof(double);      // + Inf padding (2^tmax <= 16 entries)
     const size_t curve_bytes = (size_t)S.nbins * SF_CURVE_STRIDE * sizeof(double);
@@ -127,7 +132,7 @@ int cgb_sfcc_fast_prepare(cgb_handle* h)
     int nb = 1024;
     while (nb < 32768 && seg_bytes + curve_bytes + (size_t)(2 * nb) * 2 <= budget && nb < 16 * nk) nb <<= 1;
     std::vector<unsigned short> bucket(nb);
-    const double hmin = Hk[0], range = Hk[nk - 1] - Hk[0], bw = range / nb, eps = 1e-12 * range;
+    const double hmin = Hk[knot0], range = Hk[nk - 1] - Hk[knot0], bw = range / nb, eps = 1e-12 * range;
     auto last_le = [&](double x) { return (int)(std::upper_bound(Hk.begin(), Hk.end(), x) - Hk.begin()) - 1; };
     int tmax = 0;
     for (int b = 0; b < nb; ++b) {
@@ -145,7 +150,9 @@ int cgb_sfcc_fast_prepare(cgb_handle* h)
     for (int i = 0; i < nk + 16; ++i) {
         if (i < nk) {
             int sg = std::min(i, nk - 2);
-            blob.push_back(Hk[i]); blob.push_back((Tk[sg + 1] - Tk[sg]) / (Hk[sg + 1] - Hk[sg])); blob.push_back(Tk[i]); blob.push_back(0.0);
+            double slope = (Tk[sg + 1] - Tk[sg]) / (Hk[sg + 1] - Hk[sg]);
+            if (flat && (i == 0 || i == nk - 1)) slope = 0.0;
+            blob.push_back(Hk[i]); blob.push_back(slope); blob.push_back(Tk[i]); blob.push_back(0.0);
         } else { blob.push_back(INFINITY); blob.push_back(0.0); blob.push_back(0.0); blob.push_back(0.0); }
     }
     align16();
@@ -155,7 +162,9 @@ int cgb_sfcc_fast_prepare(cgb_handle* h)
     align16();
     S.off_curve = (int)(blob.size() * sizeof(double));
     long double worst = 0.0L;
-    for (int b = 0; b < S.nbins; ++b) {
+    blob.push_back(S.thw_thawed);
+    for (int j = 1; j < SF_CURVE_STRIDE; ++j) blob.push_back(0.0);
+    for (int b = 0; b < S.nbins - 1; ++b) {
         int E = Emin + (b >> 4), k = b & 15;
         double c[SF_CURVE_STRIDE] = {0};
         fit_bin(f, E, k, c);
@@ -173,8 +182,8 @@ int cgb_sfcc_fast_prepare(cgb_handle* h)
     if (!(worst <= 1e-13L)) return CGB_OK;
     align16();
     S.blob_bytes = (int)(blob.size() * sizeof(double));
-    S.hmin = hmin; S.invbw = nb / range; S.hlo = Hk[0]; S.hhi = Hk[nk - 1];
-    S.nk = nk; S.nb = nb; S.extrap_flat = (it->second.extrap == CGB_EXTRAP_FLAT);
+    S.hmin = hmin; S.invbw = nb / range;
+    S.nk = nk; S.nb = nb;
     S.fit_error = (double)worst;
     double* d_blob = nullptr;
     int rc = dev_upload(h, &d_blob, blob);

@@ -107,13 +107,19 @@ def test_fast_path_matches_general_kernel():
 
 
 def test_fast_path_flat_extrapolation_and_small_grids(orc):
-    for grid, ex in ((cg.DefaultGrid_10cm, "flat"), (cg.DefaultGrid_1m, "line"), (cg.Grid(np.linspace(0.0, 3.0, 7)), "line"),
-                     (cg.DefaultGrid_2cm, "line")):
+    # dtmax below the diffusion limit of the finest cells of each grid (2 cm: ~150 s), so that the strict gate applies
+    for name, grid, ex, dtmax in (("10cm", cg.DefaultGrid_10cm, "flat", 600.0), ("1m", cg.DefaultGrid_1m, "line", 3600.0),
+                                  ("6 cells", cg.Grid(np.linspace(0.0, 3.0, 7)), "flat", 3600.0), ("2cm", cg.DefaultGrid_2cm, "line", 100.0)):
         tile = _tile(3, "dallamico", 2.0, 1.6, grid=grid, extrap=ex)
         H0 = cg.initialcondition(tile)
         H0[:, 1] += 3.0e8 * (np.arange(H0.shape[0]) % 3 == 0)          # thawed cells far above the last knot
-        eng = cg.Engine(tile, dtmax=600.0)
-        _check_advance(orc, tile, eng, H0, 0.0, [3600.0, DAY], dtmax=600.0)
+        H0[:, 2] -= 2.0e8 * (np.arange(H0.shape[0]) % 4 == 1)          # and cells far below the first one
+        eng = cg.Engine(tile, dtmax=dtmax)
+        try:
+            w = _check_advance(orc, tile, eng, H0, 0.0, [3600.0, DAY], dtmax=dtmax)
+        except AssertionError as e:
+            raise AssertionError(f"grid {name}, extrapolation {ex}: {e}") from e
+        print(f"grid {name} ({ex}):", w)
         eng.close()
 
 
