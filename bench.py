@@ -28,7 +28,7 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for _p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short runs of the other BASELINE configurations")
+    ap.add_argument("--cpu-columns", type=int, default=1024, help="column sample of the CPU legs")
     return ap.parse_args()
 
 
@@ -56,6 +58,20 @@ def peaks():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic():
+    """DRAM bytes per launch of the headline kernel from the committed `ncu --set full` capture of THIS bench command on the
+    final build (profiles/r2_ncu_bench_fast_kernel.json, written by scripts/ncu_traffic.py); None when there is no capture."""
+    path = os.path.join(ROOT, "profiles", "r2_ncu_bench_fast_kernel.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return (int(d["dram_bytes_read"] + d["dram_bytes_write"]),
+                f"dram__bytes_read.sum + dram__bytes_write.sum of the longest launch of {d['kernel'].split('(')[0]} in an ncu --set full capture of "
+                f"`{d['command']}` (profiles/r2_ncu_bench_fast_kernel.json)", d.get("fp64_pipe_pct"))
+    except Exception:
+        return None, "no ncu --set full capture of the bench command committed", None
 
 
 class ClockSampler:
@@ -115,8 +131,8 @@ class ClockSampler:
 
 
 def make_tile(columns, total_days, seed):
-    import common
-    return common.samoylov_freew_tile(ncolumns=columns, seed=seed, forcing_days=int(total_days) + 3)
+    from cryogrid_jl_b200 import presets
+    return presets.samoylov_freew_tile(ncolumns=columns, seed=seed, forcing_days=int(total_days) + 3)
 
 
 def host_threads():
@@ -128,13 +144,16 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_leg(tile, H0, seconds, nthreads=0, days=None):
-    """Oracle restatement (OpenMP over columns) on a bounded column sample; returns (cell_steps/s, dict)."""
+def cpu_leg(tile, H0, seconds, nthreads=0, days=None, ncol=1024):
+    """The reference's CPU path as restated by the oracle, timing copy (oracle/libcg_oracle_fast.so: -O3, AVX2 + FMA, hoisted
+    invariants), OpenMP over columns on all host threads, on a bounded sample: `ncol` columns (>= 10^3 by default) for as many
+    simulated days as fit the time budget.  Returns (cell_steps/s, dict)."""
     import oracle as orc
+    orc.use_timing_copy(True)
     if nthreads == 0:
         nthreads = host_threads()
     cores = nthreads
-    ncol = min(tile.M, max(cores, 1) * 2)
+    ncol = min(tile.M, max(ncol, 2 * cores))
     cols = np.arange(ncol)
     prepared = orc.batch_columns(tile, cols)
     N = tile.grid.ncells
@@ -147,10 +166,92 @@ def cpu_leg(tile, H0, seconds, nthreads=0, days=None):
         el = time.perf_counter() - t0
         return int(ns.sum()) * N, el
     if days is None:
-        cs, el = run(2.0)                                   # calibrate
-        days = max(2.0, min(365.0, 2.0 * seconds / max(el, 1e-3)))
+        cs, el = run(0.05)                                  # calibrate on 1.2 simulated hours
+        days = max(0.05, min(365.0, 0.05 * seconds / max(el, 1e-3)))
     cs, el = run(days)
-    return cs / el, {"cores": int(cores), "sample": f"{ncol} columns x {days:.0f} simulated days (first days of the cfg2 run)", "seconds": el}
+    return cs / el, {"cores": int(cores), "sample": f"{ncol} columns x {days:.2f} simulated days (start of the cfg2 run), oracle timing copy "
+                     "(-O3 -march=x86-64-v3, OpenMP over columns)", "seconds": el}
+
+
+def _timed_advance(eng, targets):
+    eng.profile_enable(True); eng.profile_read()
+    s0 = eng.stats()
+    for tt in targets:
+        eng.advance_to(tt, sync=False)
+    eng.synchronize()
+    n, ms = eng.profile_read()
+    eng.profile_enable(False)
+    s1 = eng.stats()
+    return s1["cell_steps"] - s0["cell_steps"], ms / 1e3, s1
+
+
+def side_configs(device, peak):
+    """Short, driver-observable runs of the OTHER BASELINE.json configurations (the headline workload is cfg2): for each one the
+    device throughput over a few simulated days at full column count, its HBM-equivalent fraction (SURVEY 8d bytes per cell-step)
+    and a parity spot check of the same physics on 8 columns against the oracle (one RHS evaluation, relative error scaled as in
+    SURVEY 8d; LiteImplicit: one daily step, relative enthalpy error)."""
+    import cryogrid_jl_b200 as cg
+    from cryogrid_jl_b200 import presets
+    import oracle as orc
+    orc.use_timing_copy(False)            # parity spot checks use the PARITY oracle (-O2 -ffp-contract=off)
+    out = {}
+
+    def heat_rhs_parity(tile, dtmax=3600.0):
+        H0 = cg.initialcondition(tile)
+        eng = cg.Engine(tile, dtmax=dtmax, device=device); eng.set_state(H0, 0.0)
+        dH = eng.rhs(0.0); eng.close()
+        worst = 0.0
+        for c in range(tile.M):
+            oc = orc.OracleColumn(tile, c)
+            dref, _ = oc.rhs(H0[:, c], 0.0)
+            worst = max(worst, presets.rhs_error(dH[:, c], dref, oc.work.get("jH"), tile.grid.dedges))
+        return worst
+
+    def entry(name, cs, sec, bytes_per, columns, cells, parity, note, stats):
+        out[name] = {"value": cs / sec, "unit": "cell-steps/s", "hbm_equiv_frac": cs / sec * bytes_per / (peak * 1e9), "bytes_per_cell_step": bytes_per,
+                     "columns": columns, "cells": cells, "steps_per_column": stats["column_steps"] / columns, "status_or": stats["status_or"],
+                     "parity_8col_vs_oracle": parity, "note": note}
+
+    # cfg1b: examples/heat_sfcc_constantbc.jl with the SFCC wired in, ONE column (latency of a single column, not throughput)
+    tile = presets.sfcc_tile(ncolumns=1, kind="painterkarra", solver="lut")
+    eng = cg.Engine(tile, dtmax=900.0, device=device); eng.set_state(cg.initialcondition(tile), 0.0); eng.advance_to(DAY)
+    cs, sec, st = _timed_advance(eng, [DAY * d for d in range(2, 12)]); eng.close()
+    entry("cfg1b", cs, sec, 16.0, 1, tile.grid.ncells, heat_rhs_parity(presets.sfcc_tile(ncolumns=8, kind="painterkarra", solver="lut"), 900.0),
+          "single SFCC column (PainterKarra a=1 n=2, presolver LUT), constant 10 W/m2 in/out, dtmax 900 s, 10 days; RHS parity", st)
+    # cfg3: LiteImplicitEuler ensemble, 10^5 members, initial condition on the device
+    M = 100000
+    tile = presets.lite_ensemble_tile(ncolumns=M, seed=1234, forcing_days=60)
+    eng = cg.Engine(tile, stepper="lite", device=device); eng.initialcondition(0.0); eng.advance_to(5 * DAY)
+    cs, sec, st = _timed_advance(eng, [DAY * d for d in range(10, 41, 5)]); eng.close()
+    t8 = presets.lite_ensemble_tile(ncolumns=8, seed=1234, forcing_days=60)
+    H8 = cg.initialcondition(t8)
+    e8 = cg.Engine(t8, stepper="lite", device=device); e8.set_state(H8, 0.0); e8.advance_to(DAY); Hg = e8.get_state(); e8.close()
+    par = max(float(np.max(np.abs(Hg[:, c] - orc.OracleColumn(t8, c).lite_advance(H8[:, c], 0.0, DAY, DAY)[0]) / (np.abs(Hg[:, c]) + 1e3))) for c in range(8))
+    entry("cfg3", cs, sec, 16.0, M, tile.grid.ncells, par,
+          "LiteImplicitEuler parameter ensemble (cglite_parameter_ensembles-style), 35 daily steps, 5 per launch, ThermalSteadyStateInit on the device; "
+          "parity = relative enthalpy error after one daily step", st)
+    # cfg4: SFCC DallAmico -- presolver LUT of one soil class (SFCC fast path) and per-column parameters (on-device Newton)
+    for name, variant, note in (("cfg4_lut", "lut", "10^5 SFCC DallAmico columns of one soil class through the presolver LUT (k_heat_sfcc_fast), 3 days"),
+                                ("cfg4_newton", "newton", "10^5 SFCC DallAmico columns with per-column alpha, n, porosity, organic fraction (on-device Newton), 3 days")):
+        tile = presets.cfg4_tile(M, variant)
+        eng = cg.Engine(tile, device=device); eng.set_state(cg.initialcondition(tile), 0.0); eng.advance_to(DAY)
+        cs, sec, st = _timed_advance(eng, [DAY * d for d in range(2, 5)]); eng.close()
+        entry(name, cs, sec, 16.0, M, tile.grid.ncells, heat_rhs_parity(presets.cfg4_tile(8, variant)), note + "; RHS parity", st)
+    # cfg5: coupled heat + salt
+    tile = presets.cfg5_tile(M)
+    eng = cg.SaltEngine(tile, device=device); eng.set_state(tile.initialcondition(), 0.0); eng.advance_to(DAY)
+    cs, sec, st = _timed_advance(eng, [DAY * d for d in range(2, 5)]); eng.close()
+    t8 = presets.cfg5_tile(8)
+    u8 = t8.initialcondition(); rng = np.random.default_rng(1)
+    u8[0] += rng.uniform(-3.0, 1.5, u8[0].shape); u8[1] += rng.uniform(0.0, 800.0, u8[1].shape)
+    e8 = cg.SaltEngine(t8, device=device); e8.set_state(u8, 0.0); du = e8.rhs(0.0); e8.close()
+    par = 0.0
+    for c in range(8):
+        dT, dc = orc.OracleSaltColumn(t8, c).rhs(u8[0, :, c], u8[1, :, c])
+        par = max(par, float(np.max(np.abs(du[0, :, c] - dT)) / np.max(np.abs(dT))), float(np.max(np.abs(du[1, :, c] - dc)) / np.max(np.abs(dc))))
+    entry("cfg5", cs, sec, 32.0, M, tile.grid.ncells, par, "10^5 coupled heat + salt columns (heat_sfcc_salt_constantbc-style), 3 days; "
+          "parity = max |du - du_ref| / max |du_ref| of one RHS evaluation at a salty, partly frozen state", st)
+    return out
 
 
 def run_reference(args):
@@ -159,8 +260,9 @@ def run_reference(args):
         return
     import cryogrid_jl_b200 as cg
     import oracle as orc
+    orc.use_timing_copy(True)
     cores = host_threads()
-    ncol = max(cores, 1) * 2
+    ncol = max(args.cpu_columns, 2 * cores)
     tile = make_tile(ncol, 400, seed=1)
     H0 = cg.initialcondition(tile)
     N = tile.grid.ncells
@@ -169,11 +271,11 @@ def run_reference(args):
     H = np.ascontiguousarray(H0.T); t = np.zeros(ncol); dt = np.full(ncol, 60.0)
     # calibrate the per-step sample so that the whole run stays within ~2 minutes
     t0 = time.perf_counter()
-    orc.cgeuler_advance_batch(tile, cols, H, t, dt, 1.0 * DAY, nthreads=cores, prepared=prepared)
-    per_day = time.perf_counter() - t0
+    orc.cgeuler_advance_batch(tile, cols, H, t, dt, 0.05 * DAY, nthreads=cores, prepared=prepared)
+    per_day = (time.perf_counter() - t0) / 0.05
     budget = 100.0 / max(args.steps + args.warmup, 1)
-    days = max(1.0, min(args.days_per_step, budget / max(per_day, 1e-4)))
-    cur = 1.0
+    days = max(0.02, min(args.days_per_step, budget / max(per_day, 1e-4)))
+    cur = 0.05
     for _ in range(args.warmup):
         cur += days
         orc.cgeuler_advance_batch(tile, cols, H, t, dt, cur * DAY, nthreads=cores, prepared=prepared)
@@ -185,7 +287,8 @@ def run_reference(args):
         cs += int(ns.sum()) * N
     el = time.perf_counter() - t0
     val = cs / el
-    sample = f"{ncol} columns x {days:.1f} simulated days per step (bounded sample of cfg2), oracle port of CryoGrid.jl (Julia not installed)"
+    sample = (f"{ncol} columns x {days:.2f} simulated days per step (bounded sample of cfg2), oracle port of CryoGrid.jl (Julia not installed), "
+              "timing copy -O3 -march=x86-64-v3, OpenMP over columns")
     print(json.dumps({
         "impl": "reference", "metric": "column-cell-steps/sec", "value": val, "unit": "cell-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / max(args.steps, 1), "higher_is_better": True,
@@ -297,11 +400,16 @@ def main():
                        "memory, every saved T copied back to pinned host memory (overlapped on a second stream)"}
         eng2.close()
 
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        configs = side_configs(local, peak)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, info = cpu_leg(tile, H0, args.cpu_seconds)
+        v, info = cpu_leg(tile, H0, args.cpu_seconds, ncol=args.cpu_columns)
         cpu = {"value": v, "unit": "cell-steps/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]}
 
+    traffic, traffic_src, fp64_pct = measured_traffic()
     if rank == 0:
         out = {
             "metric": "column-cell-steps/sec", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -312,11 +420,11 @@ def main():
                        "columns_per_gpu": M, "cells": N, "days_per_step": D, "l2_policy": "L2 flushed (256 MB memset) between timed steps; each step reads the "
                        "17 MB state once and keeps it in registers, so the kernel is FP64-bound either way (DESIGN.md)",
                        "wall_s_timed_region": wall_s},
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": 19319808,
-                         "peak_source": peak_src, "bytes_per_cell_step": BYTES_PER_CELL_STEP,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one bench step, profiles/r1c_ncu_k_heat_euler_fast_7_3_cubic.md",
-                         "note": "algorithmic bytes (16 B per cell-step) far exceed the DRAM traffic because the state stays in registers across the Euler steps of a launch (temporal fusion); the kernel is FP64-pipe bound (58 % busy)"},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(s1["kernel_launches"] - s0["kernel_launches"]),
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                         "peak_source": peak_src, "bytes_per_cell_step": BYTES_PER_CELL_STEP, "traffic_source": traffic_src,
+                         "note": "algorithmic bytes (16 B per cell-step) far exceed the DRAM traffic because the state stays in registers across the Euler steps of a launch (temporal fusion); the kernel is bound by the FP64 pipe" +
+                                 (f" ({fp64_pct:.0f} % busy in the capture)" if fp64_pct else "")},
+            "cpu_baseline": cpu, "e2e": e2e, "configs": configs, "gpu_launches": int(s1["kernel_launches"] - s0["kernel_launches"]),
             "clocks": clk.summary(), "cell_steps": int(total_cs), "column_steps_per_column": (s1["column_steps"] - s0["column_steps"]) / M,
         }
         print(json.dumps(out))

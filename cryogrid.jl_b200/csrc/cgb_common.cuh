@@ -107,13 +107,12 @@ struct Dev {
 
 // ---- SFCC fast path (cgb_euler_sfcc_fast.cuh): tables of the unique soil class
 constexpr int SF_CURVE_STRIDE = 10;    // doubles per bin: 8 coefficients + 2 of padding (80 B rows: LDS.128 bank skew)
-constexpr int SF_SEG_STRIDE = 4;       // doubles per presolver segment: H_i, slope_i, T_i, pad
 
 // Everything the kernel needs about the (unique) soil class; passed by value -> constant bank.
 struct SfccFast {
     // presolver interpolant
-    double hmin, invbw;        // bucket = (int)((H - hmin) * invbw), clamped to [0, nb-1]
-    int nk, nb, nbins, _pad0;
+    double boff, invbw;        // bucket = (unsigned)(H * invbw + boff) with boff = -Hmin * invbw, saturated to [0, nb-1]
+    int nk, nkp, nb, nbins;    // knots, padded knot-array length (three arrays H, slope, T of nkp doubles each), buckets, curve rows
     // freeze curve
     double tstarK;             // T* [K]
     double thw_thawed;         // θw for T >= T*  (= θ(ψ0)); also row 0 of the curve table

@@ -39,7 +39,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_heat_sfcc_fast(const __grid_cons
         for (int i = threadIdx.x; i < S.blob_bytes / 16; i += THREADS) dst[i] = __ldg(src + i);
     }
     __syncthreads();
-    const double* __restrict__ sSeg = reinterpret_cast<const double*>(smem_raw + S.off_seg);
+    const double* __restrict__ sKH = reinterpret_cast<const double*>(smem_raw + S.off_seg);       // knot enthalpies H_i
+    const double* __restrict__ sKS = sKH + S.nkp;                                                 // segment slopes dT/dH
+    const double* __restrict__ sKT = sKS + S.nkp;                                                 // knot temperatures T_i
     const unsigned short* __restrict__ sBucket = reinterpret_cast<const unsigned short*>(smem_raw + S.off_bucket);
     const double* __restrict__ sCurve = reinterpret_cast<const double*>(smem_raw + S.off_curve);
 
@@ -47,22 +49,24 @@ __global__ void __launch_bounds__(THREADS, 1) k_heat_sfcc_fast(const __grid_cons
     const int N = P.N;
     const long long M = P.M;
 
-    // static per-cell grid constants in registers
-    double dk[CPL], idk[CPL], G[CPL], dk_up;
-    bool is_edgeN[CPL];
+    // INTERLEAVED cell -> (lane, slot) mapping: cell = slot*32 + lane.  The 32 lanes of a warp then look up 32 ADJACENT cells at a
+    // time, whose enthalpies and temperatures are close: they read the same or neighbouring table rows, which the shared-memory
+    // banks serve as broadcasts / without conflicts.  (The contiguous mapping of the FreeWater kernel made every lane read its own
+    // row: measured 109 shared-memory wavefronts per warp and cell-step for an ideal 23, LSU data pipe 92 % busy --
+    // profiles/r2c_ncu_sfcc_fast_contiguous.md.)  Price: every edge now crosses a lane (3 rotating 64-bit shuffles per cell).
+    // Static per-cell grid constants in registers: rho = dk/dk_up, Gd = (dk_up + dk)/(dxc dk_up), idk = 1/dk, so that the
+    // harmonic-mean flux  -(T - T1) k1 k G / (dk k1 + dk_up k)  [math.jl:41,141]  becomes  (T1 - T)(k1 k) Gd / (rho k1 + k).
+    double rho[CPL], Gd[CPL], idk[CPL];
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
-        int i = lane * CPL + j;
+        int i = j * 32 + lane;
         bool cell = i < N, edge = (i > 0 && i < N);
-        dk[j] = cell ? P.dk[i] : 1.0;
+        double dku = edge ? P.dk[i - 1] : 1.0;
+        rho[j] = edge ? P.dk[i] / dku : 1.0;
+        Gd[j] = edge ? P.eG[i] / dku : 0.0;
         idk[j] = cell ? P.inv_dk[i] : 0.0;
-        G[j] = edge ? P.eG[i] : 0.0;
-        is_edgeN[j] = (i == N);
     }
-    {
-        int i = lane * CPL - 1;
-        dk_up = (i >= 0 && i < N) ? P.dk[i] : 1.0;
-    }
+    const int jb = (lane == ((N - 1) & 31)) ? ((N - 1) >> 5) : -1;             // slot of the bottom cell in the lane that holds it
     const bool top_dirichlet = P.top_kind == 0, use_nf = P.use_nfactor != 0;   // bottom: Neumann, constant in time (launcher)
     const int fkind = P.top.kind;
     const int fn = P.top.n;
@@ -81,17 +85,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_heat_sfcc_fast(const __grid_cons
         double H[CPL];
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
-            int i = lane * CPL + j;
+            int i = j * 32 + lane;
             H[j] = (i < N) ? P.u[(size_t)i * M + col] : 0.0;
         }
         double t = P.t[col];
         double dt = P.dt[col];
         const double nf = P.nf[col], nt = P.nt[col], toff = P.top_offset[col];
         const double vbot = P.bot_value ? P.bot_value[col] : P.bot.value;
-        double bflux[CPL];
-#pragma unroll
-        for (int j = 0; j < CPL; ++j) bflux[j] = is_edgeN[j] ? vbot : 0.0;
-        const double bflux_next = (lane * CPL + CPL == N) ? vbot : 0.0;
         int status = 0;
         long long nsteps = 0;
         int fidx = 0;
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_heat_sfcc_fast(const __grid_cons
             for (int j = 0; j < CPL; ++j) {
                 // bucket of H (flat extrapolation is part of the table: zero-slope end segments, see cgb_tu_sfcc_fast.cu); the
                 // unsigned conversion saturates negative arguments to 0
-                unsigned b = min(__double2uint_rz((H[j] - S.hmin) * S.invbw), (unsigned)(S.nb - 1));
+                unsigned b = min(__double2uint_rz(fma(H[j], S.invbw, S.boff)), (unsigned)(S.nb - 1));
                 wd[j] = sBucket[b];
                 lo[j] = (int)(wd[j] & 0xfffu);
                 trips = max(trips, wd[j]);
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_heat_sfcc_fast(const __grid_cons
 #pragma unroll
                     for (int j = 0; j < CPL; ++j) {
                         int mid = (lo[j] + hi[j] + 1) >> 1;
-                        bool p = sSeg[mid * SF_SEG_STRIDE] <= H[j];         // +Inf padded beyond the last knot
+                        bool p = sKH[mid] <= H[j];                          // +Inf padded beyond the last knot
                         lo[j] = p ? mid : lo[j];
                         hi[j] = p ? hi[j] : mid - 1;
                     }
@@ -160,9 +160,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_heat_sfcc_fast(const __grid_cons
             double r[CPL];
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
-                const double2 hs = *reinterpret_cast<const double2*>(sSeg + lo[j] * SF_SEG_STRIDE);      // H_i, slope_i
-                const double Ti = sSeg[lo[j] * SF_SEG_STRIDE + 2];
-                T[j] = fma(H[j] - hs.x, hs.y, Ti);
+                T[j] = fma(H[j] - sKH[lo[j]], sKS[lo[j]], sKT[lo[j]]);
                 // u = T* - TK with the reference's rounding sequence (TK = T + 273.15 first)
                 const double u = S.tstarK - (T[j] + 273.15);
                 const int uh = __double2hiint(u), ul = __double2loint(u);
@@ -178,10 +176,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_heat_sfcc_fast(const __grid_cons
                 const double* cf = sCurve + bin[j] * SF_CURVE_STRIDE;
                 const double2 c01 = *reinterpret_cast<const double2*>(cf), c23 = *reinterpret_cast<const double2*>(cf + 2);
                 const double2 c45 = *reinterpret_cast<const double2*>(cf + 4), c67 = *reinterpret_cast<const double2*>(cf + 6);
-                double p = fma(c67.y, r[j], c67.x);
-                p = fma(p, r[j], c45.y); p = fma(p, r[j], c45.x);
-                p = fma(p, r[j], c23.y); p = fma(p, r[j], c23.x);
-                p = fma(p, r[j], c01.y); p = fma(p, r[j], c01.x);
+                // Estrin-like split of the degree-7 Horner chain into two chains of 3 (shorter dependency chain)
+                const double r2 = r[j] * r[j];
+                double pe = fma(c67.x, r2, c45.x), po = fma(c67.y, r2, c45.y);
+                pe = fma(pe, r2, c23.x); po = fma(po, r2, c23.y);
+                pe = fma(pe, r2, c01.x); po = fma(po, r2, c01.y);
+                const double p = fma(po, r[j], pe);
                 if (SAVE) thw[j] = p;
                 const double sk = fma(S.dK, p, S.kb);
                 kc[j] = sk * sk;
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_heat_sfcc_fast(const __grid_cons
                 // last step of the interval: the reference saves the cache of this RHS evaluation (state BEFORE the step)
 #pragma unroll
                 for (int j = 0; j < CPL; ++j) {
-                    int i = lane * CPL + j;
+                    int i = j * 32 + lane;
                     if (i < N) {
                         size_t o = (size_t)kt * TG.save_stride + (size_t)i * M + col;
                         if (saveT) saveT[o] = T[j];
@@ -207,25 +207,31 @@ __global__ void __launch_bounds__(THREADS, 1) k_heat_sfcc_fast(const __grid_cons
                     }
                 }
             }
-            double Tup = __shfl_up_sync(FULL, T[CPL - 1], 1);
-            double kup = __shfl_up_sync(FULL, kc[CPL - 1], 1);
-            double je[CPL + 1];
+            // ---- flux through the UPPER edge of every local cell; the upper neighbour is the previous lane's cell of the same slot
+            // (lane 0: lane 31's cell of the previous slot = the value rotated in one slot earlier)
+            double je[CPL];
+            double Tprev = 0.0, kprev = 1.0;
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
-                double T1 = (j == 0) ? Tup : T[j - 1];
-                double k1 = (j == 0) ? kup : kc[j - 1];
-                double w1 = (j == 0) ? dk_up : dk[j - 1];
-                double den = fma(dk[j], k1, w1 * kc[j]);
-                double q = ((T1 - T[j]) * (k1 * kc[j])) * G[j];
-                je[j] = fma(q, rcp_fast3(den), bflux[j]);
+                const double Tr = __shfl_sync(FULL, T[j], (lane + 31) & 31), kr = __shfl_sync(FULL, kc[j], (lane + 31) & 31);
+                const double T1 = (lane == 0) ? Tprev : Tr, k1 = (lane == 0) ? kprev : kr;
+                Tprev = Tr; kprev = kr;
+                const double den = fma(rho[j], k1, kc[j]);
+                const double q = ((T1 - T[j]) * (k1 * kc[j])) * Gd[j];       // Gd == 0 on the top edge and beyond the bottom cell
+                je[j] = q * rcp_fast3(den);
             }
-            if (lane == 0) je[0] = top_dirichlet ? (kc[0] * (vtop - T[0])) * P.ctop : vtop;
-            je[CPL] = __shfl_down_sync(FULL, je[0], 1);
-            if (bflux_next != 0.0 || lane == 31) je[CPL] = bflux_next;
+            if (lane == 0) je[0] = top_dirichlet ? (kc[0] * (vtop - T[0])) * P.ctop : vtop;   // heat_bc.jl:9-17 / methods.jl:156
+            // ---- divergence, limiter reduction, Euler update; the lower edge is the next lane's upper edge of the same slot
+            // (lane 31: lane 0's edge of the NEXT slot), the bottom cell takes the Neumann value (heat_bc.jl:32-35)
             double ad[CPL];
+            double jn[CPL];
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) jn[j] = __shfl_sync(FULL, je[j], (lane + 1) & 31);
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
-                double dH = (je[j] - je[j + 1]) * idk[j];
+                double jlow = (lane == 31) ? ((j + 1 < CPL) ? jn[j + 1 < CPL ? j + 1 : j] : 0.0) : jn[j];
+                if (j == jb) jlow = vbot;
+                const double dH = (je[j] - jlow) * idk[j];
                 ad[j] = fabs(dH);
                 H[j] = fma(dt, dH, H[j]);                                            // basic_solvers.jl:66
             }
@@ -254,7 +260,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_heat_sfcc_fast(const __grid_cons
         }
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
-            int i = lane * CPL + j;
+            int i = j * 32 + lane;
             if (i < N) P.u[(size_t)i * M + col] = H[j];
         }
         if (lane == 0) {

@@ -125,7 +125,8 @@ int cgb_sfcc_fast_prepare(cgb_handle* h)
     S.nbins = (Emax + 1 - Emin) * 16 + 1;                 // + row 0: the thawed constant
     S.idx_base = ((Emin + 1023) << 4) - 1;
     // presolver buckets: as many as fit (power of two), same construction as the general path (cgb_api.cu finalize)
-    const size_t seg_bytes = (size_t)(nk + 16) * SF_SEG_STRIDE * sizeof(double);      // + Inf padding (2^tmax <= 16 entries)
+    const int nkp = (nk + 16 + 1) & ~1;                                               // + Inf padding (2^tmax <= 16 entries), even
+    const size_t seg_bytes = (size_t)nkp * 3 * sizeof(double);
     const size_t curve_bytes = (size_t)S.nbins * SF_CURVE_STRIDE * sizeof(double);
     const size_t budget = 200 * 1024;
     if (seg_bytes + curve_bytes + 2 * 1024 > budget) return CGB_OK;
@@ -147,13 +148,14 @@ int cgb_sfcc_fast_prepare(cgb_handle* h)
     std::vector<double> blob;
     auto align16 = [&]() { while ((blob.size() * sizeof(double)) % 16) blob.push_back(0.0); };
     S.off_seg = 0;
-    for (int i = 0; i < nk + 16; ++i) {
+    blob.assign((size_t)nkp * 3, 0.0);
+    for (int i = 0; i < nkp; ++i) {
         if (i < nk) {
             int sg = std::min(i, nk - 2);
             double slope = (Tk[sg + 1] - Tk[sg]) / (Hk[sg + 1] - Hk[sg]);
             if (flat && (i == 0 || i == nk - 1)) slope = 0.0;
-            blob.push_back(Hk[i]); blob.push_back(slope); blob.push_back(Tk[i]); blob.push_back(0.0);
-        } else { blob.push_back(INFINITY); blob.push_back(0.0); blob.push_back(0.0); blob.push_back(0.0); }
+            blob[i] = Hk[i]; blob[nkp + i] = slope; blob[2 * nkp + i] = Tk[i];
+        } else blob[i] = INFINITY;
     }
     align16();
     S.off_bucket = (int)(blob.size() * sizeof(double));
@@ -182,8 +184,8 @@ int cgb_sfcc_fast_prepare(cgb_handle* h)
     if (!(worst <= 1e-13L)) return CGB_OK;
     align16();
     S.blob_bytes = (int)(blob.size() * sizeof(double));
-    S.hmin = hmin; S.invbw = nb / range;
-    S.nk = nk; S.nb = nb;
+    S.invbw = nb / range; S.boff = -hmin * S.invbw;
+    S.nk = nk; S.nkp = nkp; S.nb = nb;
     S.fit_error = (double)worst;
     double* d_blob = nullptr;
     int rc = dev_upload(h, &d_blob, blob);

@@ -115,3 +115,9 @@ def cfg5_tile(ncolumns, seed=5):
     rng = np.random.default_rng(seed)
     benthic = rng.uniform(600.0, 1000.0, ncolumns) if ncolumns > 1 else 900.0
     return SalineTile(grid=DefaultGrid_10cm, salt_bc=SaltGradient(benthic, 0), ncolumns=ncolumns)
+
+
+def rhs_error(dH, dH_ref, jH_ref, dk):
+    """SURVEY 8d parity metric of one RHS evaluation: |dH - ref| / max(|ref|, max_j |jH| / dk) per cell, maximum over cells."""
+    scale = np.maximum(np.abs(dH_ref), np.max(np.abs(jH_ref)) / dk)
+    return float(np.max(np.abs(dH - dH_ref) / scale))

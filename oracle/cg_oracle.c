@@ -354,7 +354,17 @@ double cg_nfactor(double Tair, double nf, double nt)
  * Column RHS
  * ---------------------------------------------------------------------------------------- */
 
-void cg_work_grid(const cg_column* col, cg_work* w) { cg_grid(col->edges, col->n + 1, w->zc, w->dk, w->dxc); }
+void cg_work_grid(const cg_column* col, cg_work* w)
+{
+#ifdef CG_ORACLE_FAST
+    /* timing copy: the grid arrays of a work block are computed once per (grid, work block), not once per RHS evaluation */
+    static __thread const double* last_edges = NULL;
+    static __thread const double* last_zc = NULL;
+    if (last_edges == col->edges && last_zc == w->zc) return;
+    last_edges = col->edges; last_zc = w->zc;
+#endif
+    cg_grid(col->edges, col->n + 1, w->zc, w->dk, w->dxc);
+}
 
 /* FreeWater: Heat/heat_conduction.jl:18-30.  SFCC: Soils/soil_heat.jl:116-140. */
 void cg_freezethaw(const cg_column* col, const double* H, cg_work* w)
@@ -397,10 +407,21 @@ void cg_thermalconductivity(const cg_column* col, cg_work* w)
 {
     const cg_thermal* tp = &col->tp;
     int n = col->n;
+#ifdef CG_ORACLE_FAST
+    const double sw = sqrt(tp->kh_w), si = sqrt(tp->kh_i), sa = sqrt(tp->kh_a), sm = sqrt(tp->kh_m), so = sqrt(tp->kh_o);
+#endif
     for (int i = 0; i < n; ++i) {
         int l = col->cell_layer[i];
         double por = col->por[l], sat = col->sat[l], org = col->org[l];
+#ifdef CG_ORACLE_FAST
+        {
+            double thwi = soil_thwi(por, sat), thm = soil_thm(por, org), tho = soil_tho(por, org);
+            double s = sw * w->thw[i] + si * (thwi - w->thw[i]) + sa * (1.0 - thwi - thm - tho) + sm * thm + so * tho;
+            w->kc[i] = s * s;
+        }
+#else
         w->kc[i] = soil_thermalconductivity(tp, w->thw[i], soil_thwi(por, sat), soil_thm(por, org), soil_tho(por, org));
+#endif
         if (i > 0) w->k[i] = cg_harmonicmean(w->kc[i - 1], w->kc[i], w->dk[i - 1], w->dk[i]);
     }
     w->k[0] = w->kc[0];

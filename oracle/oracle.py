@@ -12,6 +12,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcg_oracle.so")
+FAST_LIB_PATH = os.path.join(HERE, "libcg_oracle_fast.so")   # -O3 -march=native timing copy (bench.py cpu legs only)
 
 _D = C.POINTER(C.c_double)
 _I32 = C.POINTER(C.c_int32)
@@ -59,7 +60,8 @@ class SaltWork(C.Structure):
 
 def build(force=False):
     src = [os.path.join(HERE, f) for f in ("cg_oracle.c", "cg_oracle.h", "Makefile")]
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(s) for s in src):
+    stale = lambda p: not os.path.exists(p) or os.path.getmtime(p) < max(os.path.getmtime(s) for s in src)
+    if force or stale(LIB_PATH) or stale(FAST_LIB_PATH):
         r = subprocess.run(["make", "-C", HERE, "-B"], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
@@ -67,13 +69,20 @@ def build(force=False):
 
 
 _lib = None
+_use_fast = False
+
+
+def use_timing_copy(on=True):
+    """bench.py only: bind the -O3 -march=native timing copy instead of the parity oracle (must be called before lib())."""
+    global _use_fast, _lib
+    _use_fast, _lib = bool(on), None
 
 
 def lib():
     global _lib
     if _lib is None:
         build()
-        l = C.CDLL(LIB_PATH)
+        l = C.CDLL(FAST_LIB_PATH if _use_fast else LIB_PATH)
         l.cg_flux.restype = C.c_double; l.cg_flux.argtypes = [C.c_double] * 4
         l.cg_divergence.restype = C.c_double; l.cg_divergence.argtypes = [C.c_double] * 3
         l.cg_harmonicmean.restype = C.c_double; l.cg_harmonicmean.argtypes = [C.c_double] * 4

@@ -4,10 +4,4 @@ import numpy as np
 
 import cryogrid_jl_b200 as cg
 from cryogrid_jl_b200.presets import (YEAR, DAY, unit_soil_props, fourier_tile, samoylov_freew_tile, sfcc_tile,  # noqa: F401
-                                      lite_ensemble_tile, cfg4_tile, cfg5_tile)
-
-
-def rhs_error(dH, dH_ref, jH_ref, dk):
-    """SURVEY 8d parity metric: |dH - ref| / max(|ref|, max_j |jH| / dk) per cell."""
-    scale = np.maximum(np.abs(dH_ref), np.max(np.abs(jH_ref)) / dk)
-    return np.max(np.abs(dH - dH_ref) / scale)
+                                      lite_ensemble_tile, cfg4_tile, cfg5_tile, rhs_error)
