@@ -121,6 +121,22 @@ extern "C" int cgb_set_layers(cgb_handle* h, const int32_t* cell_layer)
     return CGB_OK;
 }
 
+// Granularities finalize() actually honours, per parameter (a granularity outside this table used to be accepted and then read
+// as v[0], i.e. a per-column ensemble silently ran with member 0's value).
+static unsigned allowed_granularities(const cgb_handle* h, const char* name)
+{
+    auto bit = [](int per) { return 1u << per; };
+    const unsigned G = bit(CGB_PER_GLOBAL), L = bit(CGB_PER_LAYER), C = bit(CGB_PER_COLUMN), CL = bit(CGB_PER_COLUMN_LAYER), CELL = bit(CGB_PER_CELL);
+    const bool salt = h->cfg.physics == CGB_PHYSICS_HEAT_SALT;
+    auto is = [&](const char* a) { return std::strcmp(name, a) == 0; };
+    if (is("por")) return salt ? (G | CELL) : (G | L | C | CL);          // heat+salt: porosity profile of the single SalineGround layer
+    for (const char* n : {"sat", "org", "vg_alpha", "vg_n", "theta_res", "Tm", "beta", "omega"})
+        if (is(n)) return salt ? G : (G | L | C | CL);
+    for (const char* n : {"nf", "nt", "top_offset", "bot_value", "benthic_salt"})
+        if (is(n)) return G | C;
+    return G;   // thermal properties (kh_*, ch_*, L) and salt properties: one value for the whole batch
+}
+
 extern "C" int cgb_set_param(cgb_handle* h, const char* name, const double* values, int64_t n, int32_t per)
 {
     if (!h || !name || !values) return CGB_ERR_INVALID;
@@ -136,6 +152,9 @@ extern "C" int cgb_set_param(cgb_handle* h, const char* name, const double* valu
     case CGB_PER_CELL: want = h->N; break;
     default: CGB_FAIL(h, CGB_ERR_INVALID, "bad granularity %d", per);
     }
+    if (!(allowed_granularities(h, name) & (1u << per)))
+        CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "parameter '%s' does not support granularity %d (GLOBAL=0, LAYER=1, COLUMN=2, COLUMN_LAYER=3, CELL=4) "
+                 "with this physics; see include/cgb200.h", name, per);
     if (n != want) CGB_FAIL(h, CGB_ERR_INVALID, "parameter '%s': expected %lld values, got %lld", name, (long long)want, (long long)n);
     ParamArray& p = h->params[name];
     p.v.assign(values, values + n);
@@ -780,6 +799,30 @@ static int advance_and_save(cgb_handle* h, double t, const SaveVars& sv, double*
     return CGB_OK;
 }
 
+// (Re)allocates both staging buffers for `elems` doubles each.  stage_elems is reset BEFORE anything is freed and set only after both
+// allocations succeeded, so a failed allocation can never leave a stale size behind (a later, smaller request would otherwise pass
+// the size check and launch kernels on null buffers).
+static int ensure_staging(cgb_handle* h, size_t elems)
+{
+    if (h->stage_elems >= elems && h->d_stage[0] && h->d_stage[1]) return CGB_OK;
+    h->stage_elems = 0;
+    for (int i = 0; i < 2; ++i) {
+        if (h->d_stage[i]) cudaFree(h->d_stage[i]);
+        h->d_stage[i] = nullptr;
+    }
+    for (int i = 0; i < 2; ++i) {
+        cudaError_t e = cudaMalloc((void**)&h->d_stage[i], elems * sizeof(double));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            if (i == 1) { cudaFree(h->d_stage[0]); h->d_stage[0] = nullptr; }
+            h->d_stage[i] = nullptr;
+            CGB_FAIL(h, CGB_ERR_ALLOC, "staging buffer (%zu bytes): %s", elems * sizeof(double), cudaGetErrorString(e));
+        }
+    }
+    h->stage_elems = elems;
+    return CGB_OK;
+}
+
 extern "C" int cgb_solve_saveat(cgb_handle* h, const double* tsave, int64_t nsave, const char* vars, double* out)
 {
     if (!h || !tsave || !vars || !out || nsave < 1) return CGB_ERR_INVALID;
@@ -794,31 +837,18 @@ extern "C" int cgb_solve_saveat(cgb_handle* h, const double* tsave, int64_t nsav
     if (rc) return rc;
     if (sv.names.empty()) CGB_FAIL(h, CGB_ERR_INVALID, "no variables to save");
     size_t NM = (size_t)h->N * h->M, per_save = NM * sv.names.size();
-    if (h->stage_elems < per_save) {
-        for (int i = 0; i < 2; ++i) {
-            if (h->d_stage[i]) cudaFree(h->d_stage[i]);
-            h->d_stage[i] = nullptr;
-            cudaError_t e = cudaMalloc((void**)&h->d_stage[i], per_save * sizeof(double));
-            if (e != cudaSuccess) CGB_FAIL(h, CGB_ERR_ALLOC, "staging buffer: %s", cudaGetErrorString(e));
-        }
-        h->stage_elems = per_save;
-    }
+    rc = ensure_staging(h, per_save);
+    if (rc) return rc;
     // Device-side saveat: up to `chunk` save times per launch -- a column is carried through all of them in registers, the
     // saved fields of the chunk land contiguously in one staging buffer and leave in one copy.
     bool chunked = multi_target_path(h) && !sv.Tnow && !sv.Wnow;
     for (auto& n : sv.names) chunked = chunked && n != "H";   // H is the live state: it must be copied out after every save
     for (int64_t s = 1; chunked && s < nsave; ++s) chunked = tsave[s] > tsave[s - 1];
     if (chunked && nsave >= 2 && tsave[0] > h->t_front) {
-        const int chunk = (int)std::min<int64_t>(std::min<int64_t>(8, cgb_fast_max_targets()), nsave);
-        if (h->stage_elems < per_save * chunk) {
-            for (int i = 0; i < 2; ++i) {
-                if (h->d_stage[i]) cudaFree(h->d_stage[i]);
-                h->d_stage[i] = nullptr;
-                cudaError_t e = cudaMalloc((void**)&h->d_stage[i], per_save * chunk * sizeof(double));
-                if (e != cudaSuccess) CGB_FAIL(h, CGB_ERR_ALLOC, "staging buffer: %s", cudaGetErrorString(e));
-            }
-            h->stage_elems = per_save * chunk;
-        }
+        int chunk = (int)std::min<int64_t>(std::min<int64_t>(8, cgb_fast_max_targets()), nsave);
+        // 2 x chunk x per_save doubles of staging: halve the chunk when the device cannot hold that (10^6 columns: GBs per save)
+        while ((rc = ensure_staging(h, per_save * chunk)) != CGB_OK && chunk > 1) chunk = std::max(1, chunk / 2);
+        if (rc) return rc;
         int64_t c = 0;
         for (int64_t s0 = 0; s0 < nsave; ++c) {
             // chunks shrink towards the end so that the last (un-overlapped) device-to-host copy is a single save
@@ -828,6 +858,9 @@ extern "C" int cgb_solve_saveat(cgb_handle* h, const double* tsave, int64_t nsav
             for (size_t v = 0; v < sv.names.size(); ++v) {
                 if (sv.names[v] == "T") bT = h->d_stage[b] + v * NM; else bW = h->d_stage[b] + v * NM;
             }
+            // a column that stops early (forcing range, NaN, bad dt: status bits) leaves its remaining save slots unwritten: make them NaN
+            // (all-ones bytes) instead of stale data from an earlier chunk; callers must still check cgb_get_status
+            CUDA_TRY(h, cudaMemsetAsync(h->d_stage[b], 0xFF, (size_t)n * per_save * sizeof(double), h->stream));
             cudaEvent_t pa = nullptr, pb = nullptr;
             if (h->profiling) { cudaEventCreate(&pa); cudaEventCreate(&pb); cudaEventRecord(pa, h->stream); }
             rc = launch_multi(h, tsave + s0, n, bT, bW, (long long)per_save);
@@ -916,14 +949,8 @@ extern "C" int cgb_solve_saveat_select(cgb_handle* h, const double* tsave, int64
         if (cell_index[k] < 0 || cell_index[k] >= h->N) CGB_FAIL(h, CGB_ERR_INVALID, "cell_index[%d] = %d out of range", k, cell_index[k]);
     size_t M = (size_t)h->M, NM = (size_t)h->N * M, SM = (size_t)std::max(nsel, 0) * M;
     size_t per_save = names.size() * SM + (thawdepth_out ? M : 0);
-    if (h->stage_elems < per_save) {
-        for (int i = 0; i < 2; ++i) {
-            if (h->d_stage[i]) cudaFree(h->d_stage[i]);
-            h->d_stage[i] = nullptr;
-            if (cudaMalloc((void**)&h->d_stage[i], per_save * sizeof(double)) != cudaSuccess) CGB_FAIL(h, CGB_ERR_ALLOC, "staging buffer");
-        }
-        h->stage_elems = per_save;
-    }
+    rc = ensure_staging(h, per_save);
+    if (rc) return rc;
     int* d_rows = nullptr;
     if (nsel > 0) {
         CUDA_TRY(h, cudaMalloc((void**)&d_rows, nsel * sizeof(int)));

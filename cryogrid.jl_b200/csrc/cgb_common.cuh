@@ -106,7 +106,11 @@ struct Dev {
 };
 
 // ---- SFCC fast path (cgb_euler_sfcc_fast.cuh): tables of the unique soil class
-constexpr int SF_CURVE_STRIDE = 10;    // doubles per bin: 8 coefficients + 2 of padding (80 B rows: LDS.128 bank skew)
+constexpr int SF_CURVE_DEG = 5;        // polynomial degree per bin
+constexpr int SF_CURVE_STRIDE = 6;     // doubles per bin = coefficients (48 B rows: 8 consecutive rows are bank-conflict free for LDS.128)
+constexpr int SF_BIN_BITS = 6;         // 2^6 bins per octave of u = T* - TK
+constexpr int SF_BIN_MASK = ((1 << SF_BIN_BITS) - 1) << (20 - SF_BIN_BITS);
+constexpr int SF_BIN_HALF = 1 << (19 - SF_BIN_BITS);
 
 // Everything the kernel needs about the (unique) soil class; passed by value -> constant bank.
 struct SfccFast {
@@ -120,6 +124,8 @@ struct SfccFast {
     int _pad;
     double fit_error;          // measured max relative error of the curve table against the closed form (host, long double)
     double kb, dK;             // sqrt-sum conductivity at θw = 0, sk_w - sk_i (thermal_properties.jl:37)
+    int n2, _pad1;             // van Genuchten n == 2: closed form through one rsqrt (no curve table in the blob)
+    double kappa, x0, dth, thres; // n == 2: x = kappa max(u, 0) + x0, θw = thres + dth (1 + x²)^-1/2
     // shared-memory blob (copied verbatim from `blob`): byte offsets, all multiples of 16
     const double* blob;
     int blob_bytes, off_seg, off_bucket, off_curve;

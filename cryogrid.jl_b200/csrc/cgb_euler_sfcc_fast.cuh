@@ -12,12 +12,13 @@
 //   * every soil / curve constant is a kernel parameter (constant bank operand: no load, no register);
 //   * the presolver knots (H_i, slope_i, T_i) and their bucket index are staged ONCE per CTA in shared memory;
 //   * θw(T) is evaluated from a CURVE TABLE in shared memory: u = T* - (T + 273.15) is split by its floating-point exponent and
-//     the top 4 mantissa bits into log-spaced bins (16 per octave); in a bin θw is a degree-7 polynomial in the mantissa
-//     remainder r = m - c_k, |r| <= 1/32, fitted on the host at Chebyshev nodes of the closed form in long double and
-//     VERIFIED there against it (cgb_tu_sfcc_fast.cu): measured 2e-15 relative for van Genuchten n = 1.6, 6e-15 for n = 2,
-//     5e-14 for n = 3 -- the accuracy of a double-precision pow() chain -- with 8 FMAs and no transcendental; a class whose fit
-//     exceeds 1e-13 (very steep curves) is not eligible and runs through the general kernel.  Also checked on the device by
-//     cgb_selftest_sfcc_curve (tests/test_gpu_sfcc_fast.py).
+//     the top 6 mantissa bits into log-spaced bins (64 per octave); in a bin θw is a degree-5 polynomial in the mantissa
+//     remainder r = m - c_k, |r| <= 1/128, fitted on the host at Chebyshev nodes of the closed form in long double and
+//     VERIFIED there against it (cgb_tu_sfcc_fast.cu): measured 2e-15 relative for van Genuchten n = 1.6, 7e-15 for n = 2,
+//     5e-14 for n = 3 -- the accuracy of a double-precision pow() chain -- with 6 FMAs and no transcendental (48-byte rows:
+//     three 16-byte loads per cell; degree 7 on 16 bins per octave has the same accuracy with four); a class whose fit exceeds
+//     1e-13 (very steep curves) is not eligible and runs through the general kernel.  Also checked on the device by
+//     cgb_selftest_sfcc_curve (tests/test_gpu_sfcc_fast.py).  Van Genuchten n == 2 needs no table at all (one rsqrt).
 //     u is formed with the reference's rounding sequence (TK = T + 273.15, then T* - TK), because near T* that cancellation --
 //     not the curve evaluation -- decides the low bits of θw.
 // ~31 FP64 instructions per cell-step instead of ~125, no global memory access in the step loop.
@@ -26,7 +27,7 @@
 
 namespace cgb {
 
-template <int CPL, int THREADS, bool SAVE>
+template <int CPL, int THREADS, bool SAVE, bool N2>
 __global__ void __launch_bounds__(THREADS, 1) k_heat_sfcc_fast(const __grid_constant__ Dev P, const __grid_constant__ SfccFast S,
                                                                const __grid_constant__ FastTargets TG,
                                                                double* __restrict__ saveT, double* __restrict__ saveW)
@@ -156,6 +157,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_heat_sfcc_fast(const __grid_cons
                     }
                 }
             }
+            if (N2) {
+                // van Genuchten n == 2 (the curve of examples/heat_sfcc_constantbc.jl): θw = θres + Δθ (1 + x²)^(-1/2) with
+                // x = α|ψ0 - cfac u| for u = T* - TK > 0 and α|ψ0| above T*  --  one rsqrt, no table
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) {
+                    T[j] = fma(H[j] - sKH[lo[j]], sKS[lo[j]], sKT[lo[j]]);
+                    const double u = S.tstarK - (T[j] + 273.15);
+                    const double x = fma(S.kappa, relu_bits(u), S.x0);
+                    const double p = fma(S.dth, rsqrt_fast(fma(x, x, 1.0)), S.thres);
+                    if (SAVE) thw[j] = p;
+                    const double sk = fma(S.dK, p, S.kb);
+                    kc[j] = sk * sk;
+                }
+            } else {
             int bin[CPL];
             double r[CPL];
 #pragma unroll
@@ -166,25 +181,25 @@ __global__ void __launch_bounds__(THREADS, 1) k_heat_sfcc_fast(const __grid_cons
                 const int uh = __double2hiint(u), ul = __double2loint(u);
                 // row 0 of the curve table is the constant θw of the thawed branch: everything below the table (u tiny, zero or
                 // negative -- the sign bit makes the shifted word negative) lands there, without a select
-                bin[j] = min(max((uh >> 16) - S.idx_base, 0), S.nbins - 1);
+                bin[j] = min(max((uh >> (20 - SF_BIN_BITS)) - S.idx_base, 0), S.nbins - 1);
                 const double m = __hiloint2double((uh & 0x000fffff) | 0x3ff00000, ul);
-                const double c = __hiloint2double(0x3ff08000 | (uh & 0x000f0000), 0);
-                r[j] = m - c;                                               // exact, |r| <= 1/32 (finite for any u)
+                const double c = __hiloint2double(0x3ff00000 | (uh & SF_BIN_MASK) | SF_BIN_HALF, 0);
+                r[j] = m - c;                                               // exact, |r| <= 2^-(SF_BIN_BITS+1) (finite for any u)
             }
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
                 const double* cf = sCurve + bin[j] * SF_CURVE_STRIDE;
                 const double2 c01 = *reinterpret_cast<const double2*>(cf), c23 = *reinterpret_cast<const double2*>(cf + 2);
-                const double2 c45 = *reinterpret_cast<const double2*>(cf + 4), c67 = *reinterpret_cast<const double2*>(cf + 6);
-                // Estrin-like split of the degree-7 Horner chain into two chains of 3 (shorter dependency chain)
+                const double2 c45 = *reinterpret_cast<const double2*>(cf + 4);
+                // two interleaved Horner chains (even / odd powers): half the dependency depth of the plain chain
                 const double r2 = r[j] * r[j];
-                double pe = fma(c67.x, r2, c45.x), po = fma(c67.y, r2, c45.y);
-                pe = fma(pe, r2, c23.x); po = fma(po, r2, c23.y);
+                double pe = fma(c45.x, r2, c23.x), po = fma(c45.y, r2, c23.y);
                 pe = fma(pe, r2, c01.x); po = fma(po, r2, c01.y);
                 const double p = fma(po, r[j], pe);
                 if (SAVE) thw[j] = p;
                 const double sk = fma(S.dK, p, S.kb);
                 kc[j] = sk * sk;
+            }
             }
         };
 
@@ -284,14 +299,19 @@ __global__ void k_selftest_sfcc_curve(const __grid_constant__ SfccFast S, const 
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const double u = S.tstarK - (Tin[i] + 273.15);
         const int uh = __double2hiint(u), ul = __double2loint(u);
-        const int bin = min(max((uh >> 16) - S.idx_base, 0), S.nbins - 1);
+        if (S.n2) {
+            const double x = fma(S.kappa, relu_bits(u), S.x0);
+            out[i] = fma(S.dth, rsqrt_fast(fma(x, x, 1.0)), S.thres);
+            continue;
+        }
+        const int bin = min(max((uh >> (20 - SF_BIN_BITS)) - S.idx_base, 0), S.nbins - 1);
         const double m = __hiloint2double((uh & 0x000fffff) | 0x3ff00000, ul);
-        const double c = __hiloint2double(0x3ff08000 | (uh & 0x000f0000), 0);
+        const double c = __hiloint2double(0x3ff00000 | (uh & SF_BIN_MASK) | SF_BIN_HALF, 0);
         const double r = m - c;
         const double* cf = sCurve + bin * SF_CURVE_STRIDE;
-        double p = cf[7];
+        double p = cf[SF_CURVE_DEG];
 #pragma unroll
-        for (int k = 6; k >= 0; --k) p = fma(p, r, cf[k]);
+        for (int k = SF_CURVE_DEG - 1; k >= 0; --k) p = fma(p, r, cf[k]);
         out[i] = p;
     }
 }

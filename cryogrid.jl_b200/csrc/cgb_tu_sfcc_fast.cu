@@ -19,34 +19,33 @@ struct CurveClass {
     }
 };
 
-// degree-7 interpolating polynomial in r at 8 Chebyshev nodes of [-1/32, 1/32] (Newton form in t = 32 r, expanded)
+// degree-SF_CURVE_DEG interpolating polynomial in r at the Chebyshev nodes of [-h, h], h = 2^-(SF_BIN_BITS+1) (Newton form in
+// t = r / h, expanded to monomials of r)
 void fit_bin(const CurveClass& f, int E, int k, double* coef)
 {
+    constexpr int NC = SF_CURVE_DEG + 1, NB = 1 << SF_BIN_BITS;
     const long double PI_L = 3.14159265358979323846264338327950288L;
-    long double t[8], y[8];
-    const long double ck = 1.0L + (k + 0.5L) / 16.0L, scale = ldexpl(1.0L, E);
-    for (int j = 0; j < 8; ++j) {
-        t[j] = cosl((2 * j + 1) * PI_L / 16.0L);
-        y[j] = f(scale * (ck + t[j] / 32.0L));
+    long double t[NC], y[NC];
+    const long double ck = 1.0L + (k + 0.5L) / NB, scale = ldexpl(1.0L, E), h = 0.5L / NB;
+    for (int j = 0; j < NC; ++j) {
+        t[j] = cosl((2 * j + 1) * PI_L / (2.0L * NC));
+        y[j] = f(scale * (ck + t[j] * h));
     }
-    // divided differences
-    long double dd[8];
-    for (int j = 0; j < 8; ++j) dd[j] = y[j];
-    for (int lev = 1; lev < 8; ++lev)
-        for (int j = 7; j >= lev; --j) dd[j] = (dd[j] - dd[j - 1]) / (t[j] - t[j - lev]);
-    // expand Newton form sum dd[j] prod_{i<j} (t - t_i) into monomials of t
-    long double mono[8] = {0}, basis[9] = {0};
+    long double dd[NC];
+    for (int j = 0; j < NC; ++j) dd[j] = y[j];
+    for (int lev = 1; lev < NC; ++lev)
+        for (int j = NC - 1; j >= lev; --j) dd[j] = (dd[j] - dd[j - 1]) / (t[j] - t[j - lev]);
+    long double mono[NC] = {0}, basis[NC + 1] = {0};
     basis[0] = 1.0L;
     int deg = 0;
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < NC; ++j) {
         for (int i = 0; i <= deg; ++i) mono[i] += dd[j] * basis[i];
-        // basis *= (t - t_j)
         for (int i = deg + 1; i >= 1; --i) basis[i] = basis[i - 1] - t[j] * basis[i];
         basis[0] = -t[j] * basis[0];
         ++deg;
     }
     long double s = 1.0L;
-    for (int j = 0; j < 8; ++j) { coef[j] = (double)(mono[j] * s); s *= 32.0L; }    // t = 32 r
+    for (int j = 0; j < NC; ++j) { coef[j] = (double)(mono[j] * s); s /= h; }
 }
 
 bool all_equal(const std::vector<double>& v)
@@ -114,24 +113,28 @@ int cgb_sfcc_fast_prepare(cgb_handle* h)
     const double sk_i = std::sqrt(G("kh_i")), sk_a = std::sqrt(G("kh_a")), sk_m = std::sqrt(G("kh_m")), sk_o = std::sqrt(G("kh_o"));
     S.kb = sk_i * thwi + sk_a * tha + sk_m * thm + sk_o * tho;
     S.dK = std::sqrt(G("kh_w")) - sk_i;
-    // curve table range: below 2^Emin the curve equals its thawed value to < 1e-16 relative; above 2^10 K nothing exists
+    // van Genuchten n == 2: closed form with one rsqrt, no table
+    S.n2 = (n == 2.0);
+    S.kappa = alpha * cfac; S.x0 = std::fabs(-alpha * psi0); S.dth = thsat_e - thres; S.thres = thres;
+    // curve table range: below 2^Emin the curve equals its thawed value to < 1e-14 relative (row 0); above 2^10 K nothing exists
+    constexpr int NB = 1 << SF_BIN_BITS;
     int Emin = -70;
     for (int E = -70; E <= 8; ++E) {
         long double d = fabsl(f(ldexpl(1.0L, E)) - (long double)S.thw_thawed);
-        if (d > 5e-17L * (long double)S.thw_thawed) { Emin = E - 1; break; }
+        if (d > 1e-14L * (long double)S.thw_thawed) { Emin = E - 1; break; }
         Emin = E;
     }
     const int Emax = 9;                                   // bins cover [2^Emin, 2^(Emax+1))
-    S.nbins = (Emax + 1 - Emin) * 16 + 1;                 // + row 0: the thawed constant
-    S.idx_base = ((Emin + 1023) << 4) - 1;
+    S.nbins = S.n2 ? 0 : (Emax + 1 - Emin) * NB + 1;      // + row 0: the thawed constant
+    S.idx_base = ((Emin + 1023) << SF_BIN_BITS) - 1;
     // presolver buckets: as many as fit (power of two), same construction as the general path (cgb_api.cu finalize)
     const int nkp = (nk + 16 + 1) & ~1;                                               // + Inf padding (2^tmax <= 16 entries), even
     const size_t seg_bytes = (size_t)nkp * 3 * sizeof(double);
     const size_t curve_bytes = (size_t)S.nbins * SF_CURVE_STRIDE * sizeof(double);
-    const size_t budget = 200 * 1024;
+    const size_t budget = 224 * 1024;
     if (seg_bytes + curve_bytes + 2 * 1024 > budget) return CGB_OK;
     int nb = 1024;
-    while (nb < 32768 && seg_bytes + curve_bytes + (size_t)(2 * nb) * 2 <= budget && nb < 16 * nk) nb <<= 1;
+    while (nb < 16384 && seg_bytes + curve_bytes + (size_t)(2 * nb) * 2 <= budget && nb < 16 * nk) nb <<= 1;
     std::vector<unsigned short> bucket(nb);
     const double hmin = Hk[knot0], range = Hk[nk - 1] - Hk[knot0], bw = range / nb, eps = 1e-12 * range;
     auto last_le = [&](double x) { return (int)(std::upper_bound(Hk.begin(), Hk.end(), x) - Hk.begin()) - 1; };
@@ -164,19 +167,22 @@ int cgb_sfcc_fast_prepare(cgb_handle* h)
     align16();
     S.off_curve = (int)(blob.size() * sizeof(double));
     long double worst = 0.0L;
-    blob.push_back(S.thw_thawed);
-    for (int j = 1; j < SF_CURVE_STRIDE; ++j) blob.push_back(0.0);
+    if (!S.n2) {
+        blob.push_back(S.thw_thawed);
+        for (int j = 1; j < SF_CURVE_STRIDE; ++j) blob.push_back(0.0);
+    }
     for (int b = 0; b < S.nbins - 1; ++b) {
-        int E = Emin + (b >> 4), k = b & 15;
+        int E = Emin + (b >> SF_BIN_BITS), k = b & (NB - 1);
         double c[SF_CURVE_STRIDE] = {0};
         fit_bin(f, E, k, c);
         for (int j = 0; j < SF_CURVE_STRIDE; ++j) blob.push_back(c[j]);
-        // verify the fit where an 8-node Chebyshev interpolant errs most (between the nodes and at the bin ends), evaluated in
-        // double exactly as the kernel does
+        // verify the fit between the Chebyshev nodes and at the bin ends, evaluated in double exactly as the kernel does
         for (int q = 0; q <= 16; ++q) {
-            double r = (q - 8) / 256.0, p = c[7];
-            for (int j = 6; j >= 0; --j) p = std::fma(p, r, c[j]);
-            long double ref = f(ldexpl(1.0L, E) * (1.0L + (k + 0.5L) / 16.0L + (long double)r));
+            double r = (q - 8) / (16.0 * NB), r2 = r * r;
+            double pe = std::fma(c[4], r2, c[2]), po = std::fma(c[5], r2, c[3]);
+            pe = std::fma(pe, r2, c[0]); po = std::fma(po, r2, c[1]);
+            double p = std::fma(po, r, pe);
+            long double ref = f(ldexpl(1.0L, E) * (1.0L + (k + 0.5L) / NB + (long double)r));
             worst = std::max(worst, fabsl((long double)p - ref) / ref);
         }
     }
@@ -201,10 +207,10 @@ int cgb_sfcc_fast_prepare(cgb_handle* h)
 #endif
 constexpr int kSfThreads = CGB_SF_THREADS;
 
-template <int CPL, bool SAVE>
+template <int CPL, bool SAVE, bool N2>
 static int launch_sf_s(cgb_handle* h, const FastTargets& tg, double* saveT, double* saveW)
 {
-    auto kern = k_heat_sfcc_fast<CPL, kSfThreads, SAVE>;
+    auto kern = k_heat_sfcc_fast<CPL, kSfThreads, SAVE, N2>;
     size_t smem = (size_t)h->sf.blob_bytes;
     int blocks_per_sm = 0;
     if (smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -221,8 +227,12 @@ static int launch_sf_s(cgb_handle* h, const FastTargets& tg, double* saveT, doub
 template <int CPL>
 static int launch_sf_t(cgb_handle* h, const FastTargets& tg, double* saveT, double* saveW)
 {
-    if (saveT || saveW) return launch_sf_s<CPL, true>(h, tg, saveT, saveW);
-    return launch_sf_s<CPL, false>(h, tg, nullptr, nullptr);
+    if (h->sf.n2) {
+        if (saveT || saveW) return launch_sf_s<CPL, true, true>(h, tg, saveT, saveW);
+        return launch_sf_s<CPL, false, true>(h, tg, nullptr, nullptr);
+    }
+    if (saveT || saveW) return launch_sf_s<CPL, true, false>(h, tg, saveT, saveW);
+    return launch_sf_s<CPL, false, false>(h, tg, nullptr, nullptr);
 }
 
 int cgb_launch_sfcc_fast_multi(cgb_handle* h, const double* targets, int n, double* saveT, double* saveW, long long save_stride)

@@ -45,7 +45,10 @@ def ensemble_moments(engine, var, t):
     """Ensemble mean/variance of a diagnostic over ALL ranks' columns.  On NCCL the per-rank partial sums are produced
     by the CUDA reduction kernel directly into a device tensor (no host round trip) and all-reduced over NVLink."""
     if dist.get_backend() == "nccl":
-        buf = torch.zeros(2 * engine.N + 1, dtype=torch.float64, device=_device())
+        buf = torch.empty(2 * engine.N + 1, dtype=torch.float64, device=_device())
+        # the library writes all 2N sums on ITS stream (and synchronises it before returning); torch's stream must not have
+        # pending work on the buffer either way
+        torch.cuda.current_stream().synchronize()
         engine.ensemble_partial_device(var, t, buf.data_ptr())
         buf[-1] = float(engine.M)
         dist.all_reduce(buf, op=dist.ReduceOp.SUM)

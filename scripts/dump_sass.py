@@ -21,7 +21,8 @@ CUOBJDUMP = os.environ.get("CUOBJDUMP", "/usr/local/cuda/bin/cuobjdump")
 # file stem -> (demangled prefix, cells per lane, steps per loop trip (source-level unroll factor), note)
 KERNELS = {
     "k_heat_euler_fast_7_3": ("void cgb::k_heat_euler_fast<7, 3, true, false>(", 7, 3, "FreeWater fast path, BASELINE cfg2 (N = 218)"),
-    "k_heat_sfcc_fast_7": ("void cgb::k_heat_sfcc_fast<7, 384, false>(", 7, 2, "SFCC single-class fast path (presolver LUT + curve table in shared memory), cfg4'"),
+    "k_heat_sfcc_fast_7": ("void cgb::k_heat_sfcc_fast<7, 384, false, false>(", 7, 2, "SFCC single-class fast path (presolver LUT + curve table in shared memory), cfg4'"),
+    "k_heat_sfcc_fast_7_n2": ("void cgb::k_heat_sfcc_fast<7, 384, false, true>(", 7, 2, "SFCC single-class fast path, van Genuchten n == 2 (rsqrt closed form), cfg4''"),
     "k_heat_step_7_1": ("void cgb::k_heat_step<7, 1>(", 7, 1, "general SFCC presolver-LUT kernel (several soil classes); the body holds both the MaxDelta and the CFL variant of stage A"),
     "k_heat_step_7_4": ("void cgb::k_heat_step<7, 4>(", 7, 1, "general SFCC presolver-LUT kernel, every van Genuchten n == 2; the body holds both the MaxDelta and the CFL variant of stage A"),
     "k_heat_step_7_2": ("void cgb::k_heat_step<7, 2>(", 7, 1, "SFCC on-device Newton kernel, BASELINE cfg4 (per-column parameters)"),
