@@ -17,10 +17,9 @@ import torch
 import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, "tests")):
-    sys.path.insert(0, p)
-import common  # noqa: E402
+sys.path.insert(0, ROOT)
 import cryogrid_jl_b200 as cg  # noqa: E402
+from cryogrid_jl_b200 import presets as common  # noqa: E402
 from cryogrid_jl_b200 import distributed as D  # noqa: E402
 
 DAY = 86400.0

@@ -103,6 +103,7 @@ struct Dev {
     double maxdelta, courant, dtmin, dtmax;
     int lite_miniters, lite_maxiters; double lite_tol;
     int bot_layer_first;      // first cell of the bottom layer (heat_implicit.jl:83 quirk)
+    int tform;                // HeatBalance(:T): the state is T, dT = dH / dHdT (heat_conduction.jl:147-152, soil_heat.jl:100-113)
 };
 
 // ---- SFCC fast path (cgb_euler_sfcc_fast.cuh): tables of the unique soil class
@@ -147,6 +148,7 @@ struct Diag {
     double *k, *jH;                             // [(N+1)*M]
     double *dH;                                 // [N*M]
     double *an, *as, *ap, *bp;                  // [N*M]
+    double *dT, *Hd;                            // [N*M] temperature form: dT = dH / dHdT; H = T C + L θw (diagnostic enthalpy)
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -47,7 +47,8 @@ __device__ __forceinline__ void layer_consts(const Dev& P, long long col, int l,
         double alpha = P.vg_alpha[ix], n = P.vg_n[ix], thres = P.theta_res[ix];
         double beta = 1.0, omega = 1.0;
         if ((kind & 0xff) == 2) { beta = P.beta[ix]; omega = P.omega[ix]; }
-        double sat_e = thwi / por;
+        // temperature form: the reference calls sfcc(T; θsat) with the functor's DEFAULT saturation 1.0 (soil_heat.jl:106)
+        double sat_e = P.tform ? 1.0 : thwi / por;
         double thtot_s = sat_e * por;
         double thsat_e = fmax(thtot_s, por);
         double psi0 = vg_psi(thtot_s, thsat_e, thres, alpha, n);
@@ -59,7 +60,9 @@ __device__ __forceinline__ void layer_consts(const Dev& P, long long col, int l,
         c[LC_SAT] = sat_e;
         // sfccheatcap base (θw = 0) with the reference's (1-θsat) quirk (soil_heat.jl:13-14)
         c[LC_CBS] = P.ch_i * thwi + P.ch_a * (por - thwi) + P.ch_m * (thm * (1.0 - por)) + P.ch_o * (tho * (1.0 - por));
-        if (((kind >> 8) & 0xff) == 0) {
+        if (P.tform) {
+            // no inverse-enthalpy solver in the temperature form
+        } else if (((kind >> 8) & 0xff) == 0) {
             int id = P.table_map ? P.table_map[ix] : l;
             int off = P.lut_off[id], nk = P.lut_len[id];
             to[0] = off; to[1] = nk;
@@ -152,7 +155,13 @@ __device__ __forceinline__ void freezethaw_body(const Dev& P, const double* lc, 
                                                 double& T, double& thw, double& C, double& dHdT, double& dth, double& kc)
 {
     int kind = (MODE == 0) ? reinterpret_cast<const int*>(lc + LC_KIND)[0] : (MODE == 3 ? 0 : ((MODE == 1 || MODE == 4) ? 1 : (1 | (1 << 8))));
-    if ((kind & 0xff) == 0) {
+    if (MODE == 5 || (MODE == 0 && P.tform)) {
+        // temperature form (soil_heat.jl:100-113): H IS the temperature; θw, ∂θw∂T straight from the curve, the REGULAR heat capacity
+        T = H;
+        thw = sfcc_theta(lc, T, dth);
+        C = fma(dC, thw, lc[LC_CB]);
+        dHdT = C + dth * (P.L + T * dC);   // heat_methods.jl:105
+    } else if ((kind & 0xff) == 0) {
         // FreeWater: heat_conduction.jl:18-57 (θw = clamp(H/Lθ,0,1) θtot; T piecewise; ∂H∂T = 1e8 at T == 0)
         double x = H * lc[LC_INVLTHTOT];
         double xc = sel_min(sel_max(x, 0.0), 1.0);
@@ -430,7 +439,10 @@ __global__ void __launch_bounds__(128) k_heat_diag(const __grid_constant__ Dev P
                 if (D.dHdT) D.dHdT[o] = dHdT[j];
                 if (D.dthwdT) D.dthwdT[o] = dth[j];
                 if (D.kc) D.kc[o] = kc[j];
-                if (D.dH) D.dH[o] = (je[j] - je[j + 1]) * sInvDk[j * 32 + lane];
+                const double dHv = (je[j] - je[j + 1]) * sInvDk[j * 32 + lane];
+                if (D.dH) D.dH[o] = dHv;
+                if (D.dT) D.dT[o] = dHv / dHdT[j];                                  // temperatureflux!: heat_conduction.jl:79-84
+                if (D.Hd) D.Hd[o] = T[j] * C[j] + P.L * thw[j];                     // enthalpy(T, C, L, θw): heat_methods.jl:93
                 if (D.k) D.k[o] = ke[j];
                 if (D.jH) D.jH[o] = je[j];
                 if (i == N - 1) {

@@ -78,7 +78,7 @@ __global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, const
     const double dK = P.sk_w - P.sk_i;
     // local slot of the bottom cell (-1 / out of [0,CPL) in the lanes that do not hold it)
     const int jb = ILV ? ((lane == ((N - 1) & 31)) ? ((N - 1) >> 5) : -1) : (N - 1) - lane * CPL;
-    const bool cfl = (P.limiter == 1);
+    const bool cfl = (P.limiter == 1) || MODE == 5;   // the temperature form needs dH/dT anyway
     const bool save = (D.T != nullptr) || (D.thw != nullptr);
 
     int loff[CPL];
@@ -146,7 +146,7 @@ __global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, const
             }
             // ---- CFL limiter: min over cells of courant * (∂H∂T / kc) * Δx² (heat_conduction.jl:150-181)
             double mincfl = INFINITY;
-            if (cfl) {
+            if (P.limiter == 1) {
 #pragma unroll
                 for (int j = 0; j < CPL; ++j) {
                     double dx = sDk[j * 32 + lane];
@@ -194,6 +194,7 @@ __global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, const
                 // Bottom: Dirichlet -k[end](T_lb-T[end])/(Δk[end]/2) (heat_bc.jl:18-27) ; Neumann: value
                 if (j == jb) jlow = (P.bot_kind == 0) ? -(kc[j] * (vbot - T[j])) * P.cbot : vbot;
                 double dH = (je[j] - jlow) * sInvDk[j * 32 + lane];
+                if (MODE == 5) dH *= rcp_fast(dHdT[j]);                               // temperature form: du = dT = dH / dHdT
                 ad[j] = fabs(dH);
                 double inc = dt * dH;
                 H[j] += inc;                                                          // u += dt*du (basic_solvers.jl:66)
@@ -209,7 +210,7 @@ __global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, const
             unsigned rh = __reduce_max_sync(FULL, mh);
             unsigned rl = __reduce_max_sync(FULL, mh == rh ? ml : 0u);
             bool bad_cfl = false;
-            if (cfl) {
+            if (P.limiter == 1) {
                 bad_cfl = __any_sync(FULL, !(mincfl > 0.0));                        // <= 0 or NaN: the reference asserts (tile.jl:174)
                 mincfl = warp_min_pos(mincfl > 0.0 ? mincfl : INFINITY);
             }
@@ -225,7 +226,7 @@ __global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, const
             double mc = sel_min(sel_max(maxabs, 1e-300), 1e300);                     // keeps the reciprocal finite
             double lim = P.maxdelta * rcp_fast(mc);                                  // 2 Newton steps: correctly rounded 1/x
             if (maxabs == INFINITY) lim = INFINITY;                                  // |Δmax/inf| = 0 -> "not > 0" -> Inf (:189)
-            if (cfl) {
+            if (P.limiter == 1) {
                 lim = sel_min(lim, mincfl);                                          // Inf stays Inf (heat_conduction.jl:180)
                 if (bad_cfl) { status |= 8; lim = 0.0; }
             }

@@ -48,6 +48,7 @@ int cgb_launch_euler_step_multi(cgb_handle* h, int mode, const double* targets, 
     case 2: return launch_step_c<2>(h, tg, D);
     case 3: return launch_step_c<3>(h, tg, D);
     case 4: return launch_step_c<4>(h, tg, D);
+    case 5: return launch_step_c<5>(h, tg, D);
     default: return launch_step_c<0>(h, tg, D);
     }
 }

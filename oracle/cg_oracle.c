@@ -375,6 +375,20 @@ void cg_freezethaw(const cg_column* col, const double* H, cg_work* w)
         double por = col->por[l], sat = col->sat[l], org = col->org[l];
         const cg_freezecurve* fc = &col->fc[l];
         double thwi = soil_thwi(por, sat); /* Hydrology.watercontent, Soils/para/simple.jl:87 */
+        if (col->op == CG_OP_TEMPERATURE) {
+            /* Soils/soil_heat.jl:100-113 freezethaw!(sfcc, soil, heat::HeatBalance{<:TemperatureBased}): the state IS T.
+             * QUIRK reproduced verbatim: the curve is called as sfcc(T; θsat = porosity), i.e. with the DEFAULT saturation 1.0
+             * of the FreezeCurves functors, whatever the soil's saturation; C is the regular heatcapacity() (not sfccheatcap).
+             * FreeWater has no temperature-form method in the reference (MethodError): NaN here. */
+            double T = H[i];
+            if (fc->kind == CG_FC_FREEWATER) { w->T[i] = T; w->thw[i] = w->C[i] = w->dHdT[i] = w->dthwdT[i] = NAN; continue; }
+            double dth;
+            double thw = cg_sfcc(fc, T, 1.0, por, 0.0, &dth, NULL);
+            double C = soil_heatcapacity(tp, thw, thwi, soil_thm(por, org), soil_tho(por, org));
+            w->T[i] = T; w->thw[i] = thw; w->C[i] = C; w->dthwdT[i] = dth;
+            w->dHdT[i] = C + dth * (tp->L + T * (tp->ch_w - tp->ch_i)); /* heat_methods.jl:105 */
+            continue;
+        }
         if (fc->kind == CG_FC_FREEWATER) {
             double thw;
             cg_freewater(H[i], thwi, tp->L, &thw);
@@ -454,7 +468,7 @@ int cg_rhs(const cg_column* col, const double* H, double t, cg_work* w)
     /* computediagnostic!: heat_conduction.jl:120-126 */
     cg_freezethaw(col, H, w);
     cg_thermalconductivity(col, w);
-    if (col->op == CG_OP_ENTHALPY) {
+    if (col->op == CG_OP_ENTHALPY || col->op == CG_OP_TEMPERATURE) {
         /* interact! Top: heat_bc.jl:9-17,28-31 ; Neumann: methods.jl:156 */
         if (col->top_kind == CG_BC_DIRICHLET) w->jH[0] += cg_flux(top, w->T[0], w->dk[0] / 2.0, w->k[0]);
         else w->jH[0] += top;
@@ -464,6 +478,8 @@ int cg_rhs(const cg_column* col, const double* H, double t, cg_work* w)
         /* computeprognostic!: heat_conduction.jl:141-146 -> heatflux! :65-72 */
         cg_flux_vec(w->jH, w->T, w->dxc, w->k, n);
         cg_divergence_vec(w->dH, w->jH, w->dk, n);
+        /* temperatureflux!: heat_conduction.jl:79-84 */
+        if (col->op == CG_OP_TEMPERATURE) for (int i = 0; i < n; ++i) w->dT[i] = w->dH[i] / w->dHdT[i];
     } else {
         /* prefactors!: heat_implicit.jl:10-24 (layer interfaces :87-103 give the same terms) */
         for (int i = 0; i < n; ++i) {
@@ -514,7 +530,8 @@ double cg_timestep(const cg_column* col, const double* H, const cg_work* w)
             double v = w->dHdT[i] / w->kc[i];
             double dx = w->dk[i];
             double dt = col->courant * v * (dx * dx);
-            dt = fmin(dt, maxdelta_limit(col->maxdelta, w->dH[i]));
+            /* derivative(::TemperatureBased) = dT, derivative(::EnthalpyBased) = dH: heat_conduction.jl:163-164 */
+            dt = fmin(dt, maxdelta_limit(col->maxdelta, col->op == CG_OP_TEMPERATURE ? w->dT[i] : w->dH[i]));
             dtmax = fmin(dtmax, dt);
         }
         dtmax = isfinite(dtmax) ? dtmax : INFINITY;
@@ -539,7 +556,8 @@ int cg_cgeuler_advance_trace(const cg_column* col, double* H, double* t, double*
     int64_t k = 0;
     while (*t < t_target) {
         status |= cg_rhs(col, H, *t, w);                  /* tile(du,u,p,t0) */
-        for (int i = 0; i < n; ++i) H[i] += (*dt) * w->dH[i]; /* u += dt*du */
+        const double* du = (col->op == CG_OP_TEMPERATURE) ? w->dT : w->dH;
+        for (int i = 0; i < n; ++i) H[i] += (*dt) * du[i];    /* u += dt*du */
         if (dt_trace && k < cap) dt_trace[k] = *dt;
         ++k;
         *t = *t + *dt;
@@ -824,12 +842,12 @@ int cg_salt_advance(const cg_salt_column* col, double* T, double* c, double* t, 
  * ---------------------------------------------------------------------------------------- */
 static void work_alloc(cg_work* w, int n, double** block)
 {
-    double* p = (double*)calloc((size_t)(16 * (n + 1)), sizeof(double));
+    double* p = (double*)calloc((size_t)(17 * (n + 1)), sizeof(double));
     *block = p;
     w->T = p; p += n; w->thw = p; p += n; w->C = p; p += n; w->dHdT = p; p += n; w->dthwdT = p; p += n;
     w->kc = p; p += n; w->k = p; p += n + 1; w->jH = p; p += n + 1; w->dH = p; p += n;
     w->an = p; p += n; w->as = p; p += n; w->ap = p; p += n; w->bp = p; p += n;
-    w->zc = p; p += n; w->dk = p; p += n; w->dxc = p;
+    w->zc = p; p += n; w->dk = p; p += n; w->dxc = p; p += n; w->dT = p;
 }
 
 int cg_max_threads(void)

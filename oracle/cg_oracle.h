@@ -51,6 +51,7 @@ extern "C" {
 /* heat operator */
 #define CG_OP_ENTHALPY 0          /* Diffusion1D(:H) */
 #define CG_OP_ENTHALPY_IMPLICIT 1 /* EnthalpyImplicit */
+#define CG_OP_TEMPERATURE 2       /* Diffusion1D(:T): prognostic T, dT = dH / dHdT (heat_conduction.jl:147-152) */
 
 /* status bits returned by the steppers */
 #define CG_STATUS_OK        0
@@ -118,6 +119,7 @@ typedef struct {
     double *dH;                                /* n   */
     double *an, *as, *ap, *bp;                 /* n   (implicit coefficients) */
     double *zc, *dk, *dxc;                     /* grid: midpoints n, cell sizes n, midpoint distances n-1 */
+    double *dT;                                /* n   (temperature form: dT = dH / dHdT) */
 } cg_work;
 
 /* ---- Numerics (src/Numerics/grid.jl, math.jl) ---- */

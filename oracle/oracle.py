@@ -42,7 +42,7 @@ class Column(C.Structure):
 
 
 class Work(C.Structure):
-    _names = ("T", "thw", "C", "dHdT", "dthwdT", "kc", "k", "jH", "dH", "an", "as_", "ap", "bp", "zc", "dk", "dxc")
+    _names = ("T", "thw", "C", "dHdT", "dthwdT", "kc", "k", "jH", "dH", "an", "as_", "ap", "bp", "zc", "dk", "dxc", "dT")
     _fields_ = [(n, _D) for n in _names]
 
 
@@ -223,7 +223,7 @@ class OracleColumn:
             bot = forcing_struct(tile.bot_forcing, self.keep)
         self.col = Column(
             n=n, n_layers=nl, edges=dp(edges), cell_layer=cl.ctypes.data_as(_I32), por=dp(por), sat=dp(sat), org=dp(org),
-            fc=C.cast(fcs, C.POINTER(FreezeCurve)), tp=thermal_struct(tile.tp), op=1 if tile.implicit else 0,
+            fc=C.cast(fcs, C.POINTER(FreezeCurve)), tp=thermal_struct(tile.tp), op=1 if tile.implicit else (2 if getattr(tile, "tform", False) else 0),
             top_kind=tile.top_kind, use_nfactor=tile.use_nfactor, bot_kind=tile.bot_kind, top=top, bot=bot,
             nf=float(tile.nf[c]), nt=float(tile.nt[c]), limiter=1 if is_cfl else 0,
             maxdelta=float(lim.maxdelta.dmax if is_cfl else lim.dmax), courant=float(lim.courant_number if is_cfl else 0.5),
@@ -233,7 +233,7 @@ class OracleColumn:
     def rhs(self, H, t):
         H = f64(H)
         st = lib().cg_rhs(C.byref(self.col), dp(H), float(t), C.byref(self.work.c))
-        return self.work.get("dH"), st
+        return self.work.get("dT" if self.col.op == 2 else "dH"), st
 
     def timestep(self, H):
         H = f64(H)
