@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("CGB_LIB_PATH") or os.path.join(HERE, "lib", "libcgb20
 ABI_VERSION = 1
 OK = 0
 ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_ALLOC = -1, -2, -3, -4, -5
-PHYSICS_HEAT, PHYSICS_HEAT_SALT = 0, 1
+PHYSICS_HEAT, PHYSICS_HEAT_SALT, PHYSICS_HEAT_T = 0, 1, 2
 STEPPER_EULER, STEPPER_LITE_IMPLICIT = 0, 1
 LIMITER_MAXDELTA, LIMITER_CFL = 0, 1
 BC_DIRICHLET, BC_NEUMANN = 0, 1

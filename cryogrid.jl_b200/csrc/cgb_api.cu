@@ -281,7 +281,7 @@ static int finalize(cgb_handle* h)
     bool any_lut = false;
     for (int l = 0; l < h->nl; ++l) {
         kinds[l] = h->fc_kind[l] | (h->fc_solver[l] << 8);
-        if (h->fc_kind[l] != CGB_FC_FREEWATER && h->fc_solver[l] == CGB_SOLVER_LUT) any_lut = true;
+        if (h->fc_kind[l] != CGB_FC_FREEWATER && h->fc_solver[l] == CGB_SOLVER_LUT && h->cfg.physics != CGB_PHYSICS_HEAT_T) any_lut = true;
     }
     int* p_k; rc |= dev_upload(h, &p_k, kinds); d.fc_kind = p_k;
     // LUTs
@@ -397,6 +397,14 @@ static int finalize(cgb_handle* h)
             }
         } else if (w == 0) d.top_inv_dt = nullptr;
         (w == 0 ? d.top : d.bot) = F;
+    }
+    d.tform = (h->cfg.physics == CGB_PHYSICS_HEAT_T);
+    if (d.tform) {
+        if (h->cfg.stepper != CGB_STEPPER_EULER || h->cfg.limiter != CGB_LIMITER_CFL)
+            CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "HeatBalance(:T) runs with CGEuler and the CFL limiter (heat_types.jl:17)");
+        for (int l = 0; l < h->nl; ++l)
+            if (h->fc_kind[l] != CGB_FC_DALLAMICO && h->fc_kind[l] != CGB_FC_PAINTERKARRA)
+                CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "HeatBalance(:T): layer %d needs an SFCC (FreeWater has no temperature form, soil_heat.jl:100-113)", l);
     }
     d.maxdelta = h->cfg.maxdelta; d.courant = h->cfg.courant; d.dtmin = h->cfg.dtmin; d.dtmax = h->cfg.dtmax;
     d.lite_miniters = h->cfg.lite_miniters; d.lite_maxiters = h->cfg.lite_maxiters; d.lite_tol = h->cfg.lite_tol;
@@ -643,6 +651,7 @@ static bool lite_thread_variant()
 // 3 = every layer FreeWater, 0 = mixed
 static int euler_mode(const cgb_handle* h)
 {
+    if (h->cfg.physics == CGB_PHYSICS_HEAT_T) return 5;   // temperature form: θw straight from the curve, du = dH / dHdT
     bool all_lut = true, all_newton = true;
     for (int l = 0; l < h->nl; ++l) {
         bool sf = h->fc_kind[l] != CGB_FC_FREEWATER;
@@ -663,7 +672,7 @@ static int euler_mode(const cgb_handle* h)
 // the stepping kernels that carry a column through several save times per launch (device-side saveat)
 static bool multi_target_path(const cgb_handle* h)
 {
-    if (h->cfg.physics != CGB_PHYSICS_HEAT) return false;
+    if (h->cfg.physics == CGB_PHYSICS_HEAT_SALT) return false;
     if (h->cfg.stepper == CGB_STEPPER_LITE_IMPLICIT) return !lite_thread_variant();
     return true;
 }
@@ -714,6 +723,7 @@ static int diag_slot(cgb_handle* h, const char* var, Diag& D, double** ptr, size
     std::string v(var);
     if (v == "T") D.T = s; else if (v == "thw") D.thw = s; else if (v == "C") D.C = s; else if (v == "dHdT") D.dHdT = s;
     else if (v == "dthwdT") D.dthwdT = s; else if (v == "kc") D.kc = s; else if (v == "dH") D.dH = s;
+    else if (v == "dT") D.dT = s; else if (v == "Henth") D.Hd = s;
     else if (v == "k") { D.k = s; *count = EM; } else if (v == "jH") { D.jH = s; *count = EM; }
     else if (v == "DT_an") D.an = s; else if (v == "DT_as") D.as = s; else if (v == "DT_ap") D.ap = s; else if (v == "DT_bp") D.bp = s;
     else CGB_FAIL(h, CGB_ERR_INVALID, "unknown diagnostic '%s'", var);
@@ -753,7 +763,7 @@ extern "C" int cgb_rhs(cgb_handle* h, double t, double* du_out)
         std::memset(du_out, 0, sizeof(double) * (size_t)h->N * h->M);
         return CGB_OK;
     }
-    return cgb_get_diag(h, "dH", t, du_out);
+    return cgb_get_diag(h, h->cfg.physics == CGB_PHYSICS_HEAT_T ? "dT" : "dH", t, du_out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -938,7 +948,7 @@ extern "C" int cgb_solve_saveat_select(cgb_handle* h, const double* tsave, int64
     if (!h || !tsave || !vars || nsave < 1 || (nsel > 0 && (!cell_index || !out)) || (nsel <= 0 && !thawdepth_out)) return CGB_ERR_INVALID;
     clear_stale_error("cgb_solve_saveat_select");
     if (!h->have_state) CGB_FAIL(h, CGB_ERR_INVALID, "no state: call cgb_set_state or cgb_init_* first");
-    if (h->cfg.physics != CGB_PHYSICS_HEAT) CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "cgb_solve_saveat_select: heat physics only");
+    if (h->cfg.physics == CGB_PHYSICS_HEAT_SALT) CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "cgb_solve_saveat_select: heat physics only");
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     int rc = finalize(h);
     if (rc) return rc;

@@ -99,7 +99,7 @@ class Engine(_EngineBase):
         is_cfl = hasattr(lim, "courant_number")
         cfg = L.Config(
             abi_version=L.ABI_VERSION, device=device, n_cells=N, n_layers=tile.n_layers, n_columns=M,
-            physics=L.PHYSICS_HEAT, stepper=L.STEPPER_LITE_IMPLICIT if lite else L.STEPPER_EULER,
+            physics=L.PHYSICS_HEAT_T if getattr(tile, "tform", False) else L.PHYSICS_HEAT, stepper=L.STEPPER_LITE_IMPLICIT if lite else L.STEPPER_EULER,
             limiter=L.LIMITER_CFL if is_cfl else L.LIMITER_MAXDELTA, top_kind=tile.top_kind, bot_kind=tile.bot_kind,
             use_nfactor=tile.use_nfactor,
             maxdelta=float(lim.maxdelta.dmax if is_cfl else lim.dmax), courant=float(lim.courant_number if is_cfl else 0.5),
@@ -141,7 +141,7 @@ class Engine(_EngineBase):
         any_lut = False
         for l in range(t.n_layers):
             self._check(self.lib.cgb_set_freezecurve(self.h, l, int(t.fc_kind[l]), int(t.fc_solver[l])))
-            any_lut |= t.fc_kind[l] != L.FC_FREEWATER and t.fc_solver[l] == L.SOLVER_LUT
+            any_lut |= t.fc_kind[l] != L.FC_FREEWATER and t.fc_solver[l] == L.SOLVER_LUT and not getattr(t, "tform", False)
         if any_lut:
             tabs, tmap = t.build_tables()
             for i, (Hk, Tk, ex) in enumerate(tabs):

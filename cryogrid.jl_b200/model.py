@@ -190,9 +190,13 @@ class CFL:
 
 @dataclass
 class HeatBalance:
-    op: str = "H"            # "H" = Diffusion1D(:H); "implicit" = EnthalpyImplicit
-    dtlim: Any = field(default_factory=MaxDelta)
+    op: str = "H"            # "H" = Diffusion1D(:H); "T" = Diffusion1D(:T); "implicit" = EnthalpyImplicit
+    dtlim: Any = None        # default_dtlim (heat_types.jl:17-18): MaxDelta(50 kJ) for :H, CFL(0.5, MaxDelta(Inf)) for :T
     prop: hm.ThermalProperties = field(default_factory=hm.ThermalProperties)
+
+    def __post_init__(self):
+        if self.dtlim is None:
+            self.dtlim = CFL(0.5, MaxDelta(float("inf"))) if self.op == "T" else MaxDelta()
 
 
 def EnthalpyImplicit():
@@ -290,6 +294,7 @@ class Tile:
         self.heat = heat
         self.tp = heat.prop
         self.implicit = heat.op == "implicit"
+        self.tform = heat.op == "T"           # HeatBalance(:T): the prognostic state is T (heat_conduction.jl:110-116)
         # boundary conditions
         self.top_kind, self.top_forcing, self.use_nfactor, self.nf, self.nt, self.top_offset = self._top(strat.top.bc)
         self.bot_kind, self.bot_forcing, self.bot_value = self._bottom(strat.bottom.bc)
@@ -450,7 +455,7 @@ class Tile:
 def SoilHeatTile(heatop, upperbc, lowerbc, soilprofile, inputs, *inits, grid=DefaultGrid_5cm, fcsolver=None,
                  ncolumns=1, heat=None):
     """models.jl:6-24 -- one Ground layer per soil-profile entry, shared heat operator."""
-    heat = heat or HeatBalance(op=heatop if heatop in ("H", "implicit") else "H")
+    heat = heat or HeatBalance(op=heatop if heatop in ("H", "T", "implicit") else "H")
     layers = [(z, Ground(para, heat=heat, fcsolver=fcsolver or SFCCPreSolver())) for z, para in soilprofile]
     strat = Stratigraphy((grid.edges[0], Top(upperbc)), layers, (grid.edges[-1], Bottom(lowerbc)))
     return Tile(strat, grid, inputs, *inits, ncolumns=ncolumns)
@@ -474,7 +479,7 @@ def initialcondition(tile: Tile, tspan=None):
             T[:, c] = hm.interp_profile(zk, vk[:, c], z)
         if not np.ptp(vk, axis=1).any():
             T[:] = T[:, :1]
-    return tile.enthalpy_from_T(T)
+    return T if getattr(tile, "tform", False) else tile.enthalpy_from_T(T)
 
 
 def _steadystate(tile: Tile, init: ThermalSteadyStateInit):

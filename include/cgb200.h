@@ -40,6 +40,9 @@ extern "C" {
 /* physics (what u holds) */
 #define CGB_PHYSICS_HEAT      0  /* HeatBalance(:H)  -- Physics/Heat/heat_types.jl:28-33 */
 #define CGB_PHYSICS_HEAT_SALT 1  /* SalineGround: HeatBalance(:T)+SaltMassBalance -- Physics/Salt/salt_types.jl:16-23 */
+#define CGB_PHYSICS_HEAT_T    2  /* HeatBalance(:T), heat only: u is T [degC], du = dT = dH / dHdT -- Physics/Heat/heat_conduction.jl:147-152,
+                                  * Soils/soil_heat.jl:100-113 (SFCC layers only: FreeWater has no temperature form in the reference);
+                                  * CGEuler with the CFL limiter (heat_types.jl:17, heat_conduction.jl:162-182) */
 /* stepper */
 #define CGB_STEPPER_EULER         0  /* CGEuler            -- Solvers/basic_solvers.jl:9-79 */
 #define CGB_STEPPER_LITE_IMPLICIT 1  /* LiteImplicitEuler  -- Solvers/LiteImplicit/cglite_types.jl:1-6 */
@@ -179,7 +182,7 @@ int cgb_rhs(cgb_handle* h, double t, double* du_out);
 int cgb_advance_to(cgb_handle* h, double t_target);
 int cgb_synchronize(cgb_handle* h);
 /* Diagnostic variable recomputed from the current state at time t (getvar/getvars: Tiles/tile.jl:251-262,
- * Numerics/statevars.jl:81-106).  var: T thw C dHdT dthwdT kc (N*M) | k jH (N+1)*M | dH | DT_an DT_as DT_ap DT_bp
+ * Numerics/statevars.jl:81-106).  var: T thw C dHdT dthwdT kc (N*M) | k jH (N+1)*M | dH dT Henth | DT_an DT_as DT_ap DT_bp
  * (heat+salt adds: H dT dc ds jc dthwdc).  out is a host pointer. */
 int cgb_get_diag(cgb_handle* h, const char* var, double t, double* out);
 /* solve(prob; saveat): advance through tsave[0..nsave) and write the saved variables

@@ -196,10 +196,11 @@ class OracleColumn:
         por, sat, org = f64(tile.por[:, c]), f64(tile.sat[:, c]), f64(tile.org[:, c])
         self.keep += [edges, cl, por, sat, org]
         fcs = (FreezeCurve * nl)()
-        tabs = tile.build_tables() if any(tile.fc_kind[l] != 0 and tile.fc_solver[l] == 0 for l in range(nl)) else None
+        tform = getattr(tile, "tform", False)     # temperature form: no inverse-enthalpy solver, no tables
+        tabs = tile.build_tables() if (not tform and any(tile.fc_kind[l] != 0 and tile.fc_solver[l] == 0 for l in range(nl))) else None
         for l in range(nl):
             table, ex = None, 1
-            if tile.fc_kind[l] != 0 and tile.fc_solver[l] == 0:
+            if tabs is not None and tile.fc_kind[l] != 0 and tile.fc_solver[l] == 0:
                 Hk, Tk, ex = tabs[0][tabs[1][l, c]]
                 table = (Hk, Tk)
             fcs[l] = fc_struct(tile.fc_dict(l, c), int(tile.fc_solver[l]), table, ex, self.keep)
