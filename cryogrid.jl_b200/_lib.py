@@ -60,6 +60,8 @@ SIGNATURES = {
     "cgb_set_param": (C.c_int, [_P, C.c_char_p, _D, C.c_int64, C.c_int32]),
     "cgb_set_freezecurve": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),
     "cgb_set_sfcc_table": (C.c_int, [_P, C.c_int32, _D, _D, C.c_int64, C.c_int32]),
+    "cgb_build_sfcc_tables": (C.c_int, [_P, C.c_double, C.c_double, C.c_double, C.c_int32, _I32]),
+    "cgb_get_sfcc_table": (C.c_int, [_P, C.c_int32, _D, _D, C.c_int64, _I64]),
     "cgb_set_sfcc_table_map": (C.c_int, [_P, _I32]),
     "cgb_set_forcing_table": (C.c_int, [_P, C.c_int32, _D, _D, C.c_int64]),
     "cgb_set_forcing_periodic": (C.c_int, [_P, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double]),

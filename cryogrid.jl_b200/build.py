@@ -10,7 +10,8 @@ LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, os.environ.get("CGB_LIB_NAME", "libcgb200.so"))      # developer knobs for A/B builds
 SOURCES = ["cgb_api.cu", "cgb_tu_fast.cu", "cgb_tu_sfcc_fast.cu", "cgb_tu_euler.cu", "cgb_tu_euler_diag.cu", "cgb_tu_lite.cu", "cgb_tu_lite_warp.cu",
-           "cgb_tu_salt.cu"]
+           "cgb_tu_salt.cu", "cgb_tu_presolver.cu"]
+EXTRA_FLAGS = {"cgb_tu_presolver.cu": ["-fmad=false"]}      # knots must agree with the (uncontracted) host builders to rounding
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
@@ -32,7 +33,7 @@ def build(force=False, verbose=False):
         path = os.path.join(CSRC, src)
         if not force and os.path.exists(obj) and os.path.getmtime(obj) >= _newest(headers + [path]):
             return obj, ""
-        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("CGB_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("CGB_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + EXTRA_FLAGS.get(src, []) + ["-c", path, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n" + r.stdout + r.stderr)

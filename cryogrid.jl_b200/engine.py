@@ -80,7 +80,10 @@ class Engine(_EngineBase):
     """Thin, explicit wrapper over the C ABI. All arrays crossing it are host NumPy arrays, column-fastest."""
 
     def __init__(self, tile, stepper="euler", dt0=None, dtmin=1.0, dtmax=None, device=0,
-                 miniters=2, maxiters=1000, tolerance=1e-3, columns=None):
+                 miniters=2, maxiters=1000, tolerance=1e-3, columns=None, device_tables=None):
+        """device_tables: build the SFCC presolver tables on the device (cgb_build_sfcc_tables) instead of the host loop of
+        Tile.build_tables(); default (None): when the tile has more than 16 distinct soil classes and no caller-built table."""
+        self.device_tables = device_tables
         self.lib = L.load()
         self.tile = tile
         cols = np.arange(tile.M) if columns is None else np.asarray(columns)
@@ -142,13 +145,35 @@ class Engine(_EngineBase):
         for l in range(t.n_layers):
             self._check(self.lib.cgb_set_freezecurve(self.h, l, int(t.fc_kind[l]), int(t.fc_solver[l])))
             any_lut |= t.fc_kind[l] != L.FC_FREEWATER and t.fc_solver[l] == L.SOLVER_LUT and not getattr(t, "tform", False)
-        if any_lut:
+        if any_lut and self._use_device_tables():
+            sv = next(s for l, s in enumerate(t.fcsolvers) if t.fc_kind[l] != L.FC_FREEWATER and t.fc_solver[l] == L.SOLVER_LUT)
+            n = C.c_int32(0)
+            self._check(self.lib.cgb_build_sfcc_tables(self.h, float(sv.Tmin), float(sv.errtol), float(sv.Tmax),
+                                                       L.EXTRAP_LINE if sv.extrap == "line" else L.EXTRAP_FLAT, C.byref(n)))
+            self.n_device_tables = n.value
+        elif any_lut:
             tabs, tmap = t.build_tables()
             for i, (Hk, Tk, ex) in enumerate(tabs):
                 Hk, Tk = L.as_f64(Hk), L.as_f64(Tk)
                 self._check(self.lib.cgb_set_sfcc_table(self.h, i, L.dptr(Hk), L.dptr(Tk), Hk.size, ex))
             m = np.ascontiguousarray(tmap[:, cols], dtype=np.int32)
             self._check(self.lib.cgb_set_sfcc_table_map(self.h, m.ctypes.data_as(C.POINTER(C.c_int32))))
+
+    def _use_device_tables(self):
+        t = self.tile
+        if any(getattr(s, "table", None) is not None for s in t.fcsolvers):
+            return False                                    # caller-built knots (e.g. sampled from the Julia interpolant) win
+        if self.device_tables is not None:
+            return bool(self.device_tables)
+        varying = sum(int(np.ptp(getattr(t, name)[:, self.columns], axis=1).any()) for name in ("por", "sat", "org", "vg_alpha", "vg_n"))
+        return varying > 0 and self.M > 16
+
+    def get_sfcc_table(self, table_id):
+        nk = C.c_int64(0)
+        self._check(self.lib.cgb_get_sfcc_table(self.h, int(table_id), None, None, 0, C.byref(nk)))
+        Hk = np.empty(nk.value); Tk = np.empty(nk.value)
+        self._check(self.lib.cgb_get_sfcc_table(self.h, int(table_id), L.dptr(Hk), L.dptr(Tk), nk.value, C.byref(nk)))
+        return Hk, Tk
 
     # ---- state
     def set_state(self, u, t0):

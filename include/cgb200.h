@@ -140,6 +140,14 @@ int cgb_set_freezecurve(cgb_handle* h, int32_t layer, int32_t fc_kind, int32_t s
 /* Caller-built SFCCPreSolver knots (H -> T), FreezeCurves.initialize! call site Soils/soil_heat.jl:26-36.
  * table_id in [0, 65536). */
 int cgb_set_sfcc_table(cgb_handle* h, int32_t table_id, const double* Hk, const double* Tk, int64_t nk, int32_t extrap);
+/* FreezeCurves.initialize!(solver, sfcc, hc; sat, θsat) ON THE DEVICE (call site Soils/soil_heat.jl:26-36; default solver
+ * SFCCPreSolver(Cache1D; Tmin = -60, errtol = 1e-4), Soils/ground.jl:27): builds the presolver table of every DISTINCT soil class
+ * among the (layer, column) pairs that use an SFCC with CGB_SOLVER_LUT -- one thread per class -- and installs the tables and
+ * the table map (replacing earlier cgb_set_sfcc_table / cgb_set_sfcc_table_map calls).  Call after all cgb_set_param /
+ * cgb_set_freezecurve calls.  At most 65536 classes (fully per-column parameters: use CGB_SOLVER_NEWTON). */
+int cgb_build_sfcc_tables(cgb_handle* h, double Tmin, double errtol, double Tmax, int32_t extrap, int32_t* n_tables_out);
+/* Read a table back (nk = its length; Hk, Tk of capacity cap may be NULL to query the length only). */
+int cgb_get_sfcc_table(cgb_handle* h, int32_t table_id, double* Hk, double* Tk, int64_t cap, int64_t* nk);
 /* which table each (layer, column) uses; n_layers*M entries, map[layer*M+col]; NULL => table_id = layer */
 int cgb_set_sfcc_table_map(cgb_handle* h, const int32_t* map);
 /* Boundary *value* as a function of time (Input(:Tair) via Interpolated1D: IO/forcings/providers.jl:14-33;
