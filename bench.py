@@ -135,6 +135,34 @@ def make_tile(columns, total_days, seed):
     return presets.samoylov_freew_tile(ncolumns=columns, seed=seed, forcing_days=int(total_days) + 3)
 
 
+def bind_to_gpu_numa(local):
+    """Pins this rank's CPU affinity to the NUMA node of its GPU BEFORE any pinned host buffer is allocated, so that the pages of
+    the e2e output buffers are local to the GPU's PCIe root (with floating ranks the 8 x 33 GB/s of saved fields crossed the
+    socket interconnect and the aggregate stalled near 90 GB/s: r1 SCALE e2e 0.88 at N = 8).  Best effort: returns a note."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return f"gpu {bdf}: local cpus {spec} not in this process's affinity mask"
+        os.sched_setaffinity(0, allowed)
+        try:
+            with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+                node = f.read().strip()
+        except Exception:
+            node = "?"
+        return f"gpu {bdf}: bound to {len(allowed)} cpus of NUMA node {node}"
+    except Exception as e:      # no sysfs in the container, no such attribute, ...
+        return f"not bound ({type(e).__name__}: {e})"
+
+
 def host_threads():
     """Host cores this process may use.  Not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its workers, which
     would silently turn the CPU legs (all host threads, by contract) into single-thread runs."""
@@ -316,6 +344,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: cryogrid.jl_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    numa_note = bind_to_gpu_numa(local) if world > 1 else "single GPU: not bound"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -398,8 +427,34 @@ def main():
             el, cs2 = float(a[0]), float(b[1])
         e2e = {"value": cs2 / el, "unit": "cell-steps/s", "h2d_bytes_per_step": int(pinned_u0.nbytes),
                "d2h_bytes_per_step": int((nsave + 1) * N * M * 8), "steps": e2e_steps, "ms_per_step": 1e3 * el / e2e_steps,
+               "numa": numa_note,
                "note": "solve(CryoGridProblem(saveat=1 day, savevars=T)) on the first timed window, u0 uploaded from pinned host "
                        "memory, every saved T copied back to pinned host memory (overlapped on a second stream)"}
+        # the device-side output path on the same window: only the depths users read from CryoGridOutput (out.T[Z(Near(zs))],
+        # examples/cglite_parameter_ensembles.jl:96) and the thaw depth of every column leave the device
+        cells = np.unique([int(np.argmin(np.abs(tile.grid.cells - z))) for z in (0.025, 0.5, 1.0, 2.0, 5.0, 10.0)]).astype(np.int32)
+        sel_out = torch.empty((nsave, 1, cells.size, M), dtype=torch.float64, pin_memory=True).numpy()
+        thaw_out = torch.empty((nsave, M), dtype=torch.float64, pin_memory=True).numpy()
+        tsave = t_w + DAY * np.arange(1, nsave + 1)
+
+        def run_select():
+            eng2.set_state(pinned_u0, t_w)
+            eng2.solve_saveat_select(tsave, ("T",), cells=cells, thawdepth=True, out=sel_out, thaw_out=thaw_out)
+            return eng2.stats()["cell_steps"]
+        run_select()
+        barrier()
+        t0 = time.perf_counter()
+        cs3 = sum(run_select() for _ in range(e2e_steps))
+        barrier()
+        el3 = time.perf_counter() - t0
+        te = torch.tensor([el3, float(cs3)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            a = te.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
+            b = te.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
+            el3, cs3 = float(a[0]), float(b[1])
+        e2e["select"] = {"value": cs3 / el3, "unit": "cell-steps/s", "h2d_bytes_per_step": int(pinned_u0.nbytes),
+                         "d2h_bytes_per_step": int(sel_out.nbytes + thaw_out.nbytes), "ms_per_step": 1e3 * el3 / e2e_steps,
+                         "note": "same window through cgb_solve_saveat_select: daily T at 6 depths + thaw depth per column (device-side output path)"}
         eng2.close()
 
     configs = None

@@ -38,11 +38,11 @@ def test_device_tables_match_the_oracle_builder_on_random_classes(orc):
         if len(Hd) != len(Ho):
             worst["mismatched_counts"] += 1          # a halving decision within rounding of errtol: possible, must stay rare
             continue
-        worst["dH"] = max(worst["dH"], float(np.max(np.abs(Hd - Ho) / np.maximum(np.abs(Ho), 1e3))))
+        worst["dH"] = max(worst["dH"], float(np.max(np.abs(Hd - Ho)) / np.max(np.abs(Ho))))     # knots cross H = 0: scale by the table range
         worst["dT"] = max(worst["dT"], float(np.max(np.abs(Td - To))))
     print("device presolver vs oracle builder:", worst)
     assert worst["mismatched_counts"] <= 1
-    assert worst["dH"] <= 1e-12 and worst["dT"] <= 1e-10
+    assert worst["dH"] <= 1e-14 and worst["dT"] <= 1e-10
     eng.close()
 
 
