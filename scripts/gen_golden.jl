@@ -92,9 +92,9 @@ function presolver_case(name, sfcc, por, satw, org)
     grid = Grid((0.0:1.0:10.0)u"m")
     tile = Tile(strat, grid, initializer(:T, -10.0))
     u0, du0 = initialcondition!(tile, (0.0, 86400.0))     # runs initialize_sfccsolver! -> FreezeCurves.initialize!
-    layer = tile.strat[2].val                             # parameter-stripped Ground layer
-    state = getstate(tile, u0, du0, 0.0)
-    lstate = getproperty(state, layernames(tile.strat)[2])
+    layer = tile.strat[2]                                 # layers(strat) = (top, sub..., bottom): the Ground layer
+    state = CryoGrid.Tiles.getstate(tile, u0, du0, 0.0)
+    lstate = getproperty(state, CryoGrid.Tiles.layernames(tile.strat)[2])
     solver = Soils.fcsolver(layer)
     hc = Soils.sfccheatcap(layer, lstate, 1)
     θsat = Soils.porosity(layer, lstate, 1)
