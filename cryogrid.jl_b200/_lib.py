@@ -79,6 +79,7 @@ SIGNATURES = {
     "cgb_get_diag": (C.c_int, [_P, C.c_char_p, C.c_double, _D]),
     "cgb_solve_saveat": (C.c_int, [_P, _D, C.c_int64, C.c_char_p, _D]),
     "cgb_solve_saveat_select": (C.c_int, [_P, _D, C.c_int64, C.c_char_p, _I32, C.c_int32, _D, _D]),
+    "cgb_solve_saveat_permafrost": (C.c_int, [_P, _D, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, _D, _D, _D, _D, _D]),
     "cgb_ensemble_partial": (C.c_int, [_P, C.c_char_p, C.c_double, _D, _D]),
     "cgb_device_state": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "cgb_ensemble_partial_device": (C.c_int, [_P, C.c_char_p, C.c_double, _P]),

@@ -1004,6 +1004,114 @@ extern "C" int cgb_solve_saveat_select(cgb_handle* h, const double* tsave, int64
 }
 
 // ------------------------------------------------------------------------------------------------
+// permafrost diagnostics reduced on the device over the saves of one call (Diagnostics/permafrost.jl:7-113): the saved T fields
+// never leave the GPU, only M-sized results do
+// ------------------------------------------------------------------------------------------------
+// running reductions after every save: per-cell max / min of the saved T, per-column max thaw depth (ALT) and the depth-mean T
+__global__ void __launch_bounds__(128) k_permafrost_update(const double* __restrict__ T, const double* __restrict__ zc, int N, long long M, int first,
+                                                          double Tmelt, int i_lo, int i_hi, double* __restrict__ Tmax, double* __restrict__ Tmin,
+                                                          double* __restrict__ alt, double* __restrict__ magt_out)
+{
+    long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (col >= M) return;
+    int i_frozen = -1, i_thawed = -1;
+    double Tf = 0.0, Tt = 0.0, sum = 0.0;
+    for (int i = 0; i < N; ++i) {
+        const size_t o = (size_t)i * M + col;
+        const double v = T[o];
+        if (i_frozen < 0 && v <= Tmelt) { i_frozen = i; Tf = v; }
+        if (i_thawed < 0 && v > Tmelt) { i_thawed = i; Tt = v; }
+        Tmax[o] = first ? v : fmax(Tmax[o], v);
+        Tmin[o] = first ? v : fmin(Tmin[o], v);
+        if (i >= i_lo && i <= i_hi) sum += v;
+    }
+    double td;                                                     // thawdepth, permafrost.jl:38-59
+    if (i_thawed >= 0 && i_frozen >= 0 && i_thawed < i_frozen) td = (Tmelt - Tt) * (zc[i_frozen] - zc[i_thawed]) / (Tf - Tt) + zc[i_thawed];
+    else if (i_frozen < 0) td = zc[N - 1];
+    else td = zc[0];
+    alt[col] = first ? td : fmax(alt[col], td);                    // active_layer_thickness, permafrost.jl:66-72 (max over the window)
+    if (magt_out) magt_out[col] = (i_hi >= i_lo) ? sum / (double)(i_hi - i_lo + 1) : nan("");   // mean_annual_ground_temperature, :108-113
+}
+
+// final pass: permafrost table / base (permafrost.jl:80-101, verbatim incl. the index arithmetic of permafrostbase) and the depth of
+// zero annual amplitude (:7-30) from the per-cell window max / min
+__global__ void __launch_bounds__(128) k_permafrost_final(const double* __restrict__ Tmax, const double* __restrict__ Tmin, const double* __restrict__ zc, int N,
+                                                         long long M, double Tmelt, double threshold, double* __restrict__ table, double* __restrict__ base,
+                                                         double* __restrict__ zaa)
+{
+    long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (col >= M) return;
+    int first_frozen = 0, last_frozen = -1, i_amp = -1;            // argmax of an all-false mask is the first index
+    bool found = false;
+    for (int i = 0; i < N; ++i) {
+        const size_t o = (size_t)i * M + col;
+        const bool fr = Tmax[o] < Tmelt;
+        if (fr && !found) { first_frozen = i; found = true; }
+        if (fr) last_frozen = i;
+        if (i_amp < 0 && (Tmax[o] - Tmin[o]) < threshold) i_amp = i;
+    }
+    if (table) table[col] = zc[first_frozen];
+    if (base) {
+        // z_inds = N .- argmax(reverse(mask)): r = 1-based position of the deepest frozen cell counted from the bottom (1 if none),
+        // 1-based index N - r, i.e. ONE CELL ABOVE the deepest frozen cell (reproduced verbatim; index 0 cannot occur in Julia)
+        int r = (last_frozen >= 0) ? (N - last_frozen) : 1;
+        int idx1 = N - r;
+        base[col] = zc[idx1 >= 1 ? idx1 - 1 : 0];
+    }
+    if (zaa) {
+        if (i_amp > 0) {
+            const size_t a = (size_t)(i_amp - 1) * M + col, b = (size_t)i_amp * M + col;
+            const double A1 = Tmax[a] - Tmin[a], A2 = Tmax[b] - Tmin[b];
+            zaa[col] = (threshold - A1) * (zc[i_amp] - zc[i_amp - 1]) / (A2 - A1) + zc[i_amp - 1];      // solve_depth_linear, Diagnostics.jl:16
+        } else zaa[col] = (i_amp == 0) ? zc[0] : INFINITY;
+    }
+}
+
+extern "C" int cgb_solve_saveat_permafrost(cgb_handle* h, const double* tsave, int64_t nsave, double Tmelt, double zaa_threshold, double magt_upper,
+                                           double magt_lower, double* alt, double* pf_table, double* pf_base, double* zaa, double* magt)
+{
+    if (!h || !tsave || nsave < 1) return CGB_ERR_INVALID;
+    clear_stale_error("cgb_solve_saveat_permafrost");
+    if (!h->have_state) CGB_FAIL(h, CGB_ERR_INVALID, "no state: call cgb_set_state or cgb_init_* first");
+    if (h->cfg.physics == CGB_PHYSICS_HEAT_SALT) CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "cgb_solve_saveat_permafrost: heat physics only");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = finalize(h);
+    if (rc) return rc;
+    const size_t M = (size_t)h->M, NM1 = (size_t)(h->N + 1) * M;
+    double* fullT = h->d_scratch;                       // saved T of the current save (reference-verbatim "T")
+    double* Tmax = h->d_scratch + 2 * NM1;
+    double* Tmin = h->d_scratch + 3 * NM1;
+    // cells with magt_upper <= z <= magt_lower (Z(Between(lower, upper)) on the cell midpoints)
+    int i_lo = h->N, i_hi = -1;
+    for (int i = 0; i < h->N; ++i) {
+        double z = (h->edges[i] + h->edges[i + 1]) / 2.0;
+        if (z >= magt_upper && z <= magt_lower) { i_lo = std::min(i_lo, i); i_hi = std::max(i_hi, i); }
+    }
+    double* d_small = nullptr;                          // alt, table, base, zaa [M each] + magt [nsave*M]
+    const size_t n_small = 4 * M + (magt ? (size_t)nsave * M : 0);
+    CUDA_TRY(h, cudaMalloc((void**)&d_small, n_small * sizeof(double)));
+    double *d_alt = d_small, *d_table = d_small + M, *d_base = d_small + 2 * M, *d_zaa = d_small + 3 * M, *d_magt = magt ? d_small + 4 * M : nullptr;
+    SaveVars need; need.T = true; need.names.push_back("T");
+    const unsigned grid = (unsigned)((M + 127) / 128);
+    for (int64_t s = 0; s < nsave; ++s) {
+        rc = advance_and_save(h, tsave[s], need, fullT, nullptr, nullptr, nullptr);
+        if (rc) { cudaFree(d_small); return rc; }
+        k_permafrost_update<<<grid, 128, 0, h->stream>>>(fullT, h->dev.zc, h->N, (long long)M, s == 0, Tmelt, i_lo, i_hi, Tmax, Tmin, d_alt,
+                                                         d_magt ? d_magt + (size_t)s * M : nullptr);
+        h->launches++;
+    }
+    k_permafrost_final<<<grid, 128, 0, h->stream>>>(Tmax, Tmin, h->dev.zc, h->N, (long long)M, Tmelt, zaa_threshold, d_table, d_base, d_zaa);
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    auto back = [&](double* dst, const double* src, size_t n) { if (dst && e == cudaSuccess) e = cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream); };
+    back(alt, d_alt, M); back(pf_table, d_table, M); back(pf_base, d_base, M); back(zaa, d_zaa, M); back(magt, d_magt, (size_t)nsave * M);
+    cudaError_t e2 = cudaStreamSynchronize(h->stream);
+    cudaFree(d_small);
+    if (e != cudaSuccess || e2 != cudaSuccess) CGB_FAIL(h, CGB_ERR_CUDA, "cgb_solve_saveat_permafrost: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+    return CGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // ensemble partial sums: one block per cell, coalesced over columns
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_ensemble_partial(const double* __restrict__ x, long long M, int N, double* __restrict__ out)

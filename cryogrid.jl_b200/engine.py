@@ -253,6 +253,17 @@ class Engine(_EngineBase):
             L.dptr(out) if cells.size else None, L.dptr(thaw_out) if thawdepth else None))
         return out, thaw_out
 
+    def solve_saveat_permafrost(self, tsave, Tmelt=0.0, zaa_threshold=0.5, magt_upper=0.0, magt_lower=10.0):
+        """Integrate through `tsave` and reduce the saved T on the device to the permafrost diagnostics of Diagnostics/permafrost.jl:
+        returns dict(alt, pf_table, pf_base, zaa [M each], magt [nsave, M])."""
+        tsave = L.as_f64(tsave)
+        out = {k: np.empty(self.M) for k in ("alt", "pf_table", "pf_base", "zaa")}
+        out["magt"] = np.empty((tsave.size, self.M))
+        self._check(self.lib.cgb_solve_saveat_permafrost(self.h, L.dptr(tsave), tsave.size, float(Tmelt), float(zaa_threshold), float(magt_upper),
+                                                         float(magt_lower), L.dptr(out["alt"]), L.dptr(out["pf_table"]), L.dptr(out["pf_base"]),
+                                                         L.dptr(out["zaa"]), L.dptr(out["magt"])))
+        return out
+
     def selftest_sfcc_curve(self, T):
         """θw(T) from the curve table of the SFCC single-class fast path (raises CgbError(UNSUPPORTED) if the tile does not qualify)."""
         T = L.as_f64(T); out = np.empty_like(T)

@@ -217,6 +217,17 @@ int cgb_solve_saveat(cgb_handle* h, const double* tsave, int64_t nsave, const ch
 int cgb_solve_saveat_select(cgb_handle* h, const double* tsave, int64_t nsave, const char* vars, const int32_t* cell_index,
                             int32_t nsel, double* out, double* thawdepth_out);
 
+/* Permafrost diagnostics reduced ON THE DEVICE over the saves tsave[0..nsave) of this call -- one "year" of the reference's annual
+ * collapse (Diagnostics/permafrost.jl); only M-sized results leave the GPU.  All outputs are host pointers and may be NULL:
+ *   alt[M]       active_layer_thickness  = max over the saves of Diagnostics.thawdepth        (permafrost.jl:38-72)
+ *   pf_table[M]  permafrosttable         = first cell depth whose window-max T < Tmelt        (:80-86)
+ *   pf_base[M]   permafrostbase          (verbatim index arithmetic)                           (:95-101)
+ *   zaa[M]       zero_annual_amplitude   = depth where max - min of T drops below threshold    (:7-30; Inf if never)
+ *   magt[nsave*M] mean_annual_ground_temperature = depth-mean of T between magt_upper and magt_lower at every save (:108-113)
+ * T is the reference's saved T (cache of the last RHS evaluation of each interval, see cgb_solve_saveat). */
+int cgb_solve_saveat_permafrost(cgb_handle* h, const double* tsave, int64_t nsave, double Tmelt, double zaa_threshold, double magt_upper,
+                                double magt_lower, double* alt, double* pf_table, double* pf_base, double* zaa, double* magt);
+
 /* ---- ensemble statistics / multi-GPU seams -------------------------------------------------------- */
 /* Local (this handle's columns) sums for ensemble moments of a diagnostic at the current state:
  * sum[cell] = Σ_col x, sumsq[cell] = Σ_col x^2 (N entries each, host pointers).  Ranks all-reduce these
