@@ -19,7 +19,7 @@ TOP, BOTTOM = 0, 1
 FC_FREEWATER, FC_DALLAMICO, FC_PAINTERKARRA, FC_DALLAMICOSALT = 0, 1, 2, 3
 SOLVER_LUT, SOLVER_NEWTON = 0, 1
 EXTRAP_FLAT, EXTRAP_LINE = 0, 1
-PER_GLOBAL, PER_LAYER, PER_COLUMN, PER_COLUMN_LAYER, PER_CELL = 0, 1, 2, 3, 4
+PER_GLOBAL, PER_LAYER, PER_COLUMN, PER_COLUMN_LAYER, PER_CELL, PER_CELL_COLUMN = 0, 1, 2, 3, 4, 5
 STATUS_MAXITERS, STATUS_NAN, STATUS_FORCING_RANGE, STATUS_BAD_DT = 1, 2, 4, 8
 
 

@@ -127,10 +127,13 @@ static unsigned allowed_granularities(const cgb_handle* h, const char* name)
 {
     auto bit = [](int per) { return 1u << per; };
     const unsigned G = bit(CGB_PER_GLOBAL), L = bit(CGB_PER_LAYER), C = bit(CGB_PER_COLUMN), CL = bit(CGB_PER_COLUMN_LAYER), CELL = bit(CGB_PER_CELL);
+    const unsigned CC = bit(CGB_PER_CELL_COLUMN);
     const bool salt = h->cfg.physics == CGB_PHYSICS_HEAT_SALT;
     auto is = [&](const char* a) { return std::strcmp(name, a) == 0; };
-    if (is("por")) return salt ? (G | CELL) : (G | L | C | CL);          // heat+salt: porosity profile of the single SalineGround layer
-    for (const char* n : {"sat", "org", "vg_alpha", "vg_n", "theta_res", "Tm", "beta", "omega"})
+    if (is("por")) return salt ? (G | CELL | CC) : (G | L | C | CL);     // heat+salt: porosity profile of the single SalineGround layer
+    for (const char* n : {"sat", "org", "vg_alpha", "vg_n", "theta_res", "Tm"})
+        if (is(n)) return salt ? (G | C) : (G | L | C | CL);
+    for (const char* n : {"beta", "omega"})
         if (is(n)) return salt ? G : (G | L | C | CL);
     for (const char* n : {"nf", "nt", "top_offset", "bot_value", "benthic_salt"})
         if (is(n)) return G | C;
@@ -150,10 +153,11 @@ extern "C" int cgb_set_param(cgb_handle* h, const char* name, const double* valu
     case CGB_PER_COLUMN: want = h->M; break;
     case CGB_PER_COLUMN_LAYER: want = (int64_t)h->nl * h->M; break;
     case CGB_PER_CELL: want = h->N; break;
+    case CGB_PER_CELL_COLUMN: want = (int64_t)h->N * h->M; break;
     default: CGB_FAIL(h, CGB_ERR_INVALID, "bad granularity %d", per);
     }
     if (!(allowed_granularities(h, name) & (1u << per)))
-        CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "parameter '%s' does not support granularity %d (GLOBAL=0, LAYER=1, COLUMN=2, COLUMN_LAYER=3, CELL=4) "
+        CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "parameter '%s' does not support granularity %d (GLOBAL=0, LAYER=1, COLUMN=2, COLUMN_LAYER=3, CELL=4, CELL_COLUMN=5) "
                  "with this physics; see include/cgb200.h", name, per);
     if (n != want) CGB_FAIL(h, CGB_ERR_INVALID, "parameter '%s': expected %lld values, got %lld", name, (long long)want, (long long)n);
     ParamArray& p = h->params[name];
@@ -833,15 +837,52 @@ static int ensure_staging(cgb_handle* h, size_t elems)
     return CGB_OK;
 }
 
+// heat+salt: saved variables are the prognostic T, c and any cell diagnostic of the salt path (thw, C, dHdT, kc, H, dT, dc, ...), all
+// evaluated AT the saved state (the reference's SalineGround example saves T, θw, k, dₛ: examples/heat_sfcc_salt_constantbc.jl:20)
+static int salt_solve_saveat(cgb_handle* h, const double* tsave, int64_t nsave, const char* vars, double* out)
+{
+    std::vector<std::string> names;
+    {
+        std::string s(vars), cur;
+        for (char c : s) { if (c == ',') { if (!cur.empty()) names.push_back(cur); cur.clear(); } else if (c != ' ') cur.push_back(c); }
+        if (!cur.empty()) names.push_back(cur);
+    }
+    if (names.empty()) CGB_FAIL(h, CGB_ERR_INVALID, "no variables to save");
+    for (auto& n : names)
+        if (n == "k" || n == "ds" || n == "jH" || n == "jc") CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "cgb_solve_saveat (heat+salt): cell variables only, got '%s'", n.c_str());
+    const size_t NM = (size_t)h->N * h->M, per_save = NM * names.size();
+    int rc = ensure_staging(h, per_save);
+    if (rc) return rc;
+    for (int64_t s = 0; s < nsave; ++s) {
+        const int b = (int)(s & 1);
+        rc = launch_advance(h, tsave[s]);
+        if (rc) return rc;
+        if (s >= 2) CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->stage_free[b], 0));
+        for (size_t v = 0; v < names.size(); ++v) {
+            double* dst = h->d_stage[b] + v * NM;
+            if (names[v] == "T") CUDA_TRY(h, cudaMemcpyAsync(dst, h->dev.u, NM * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+            else if (names[v] == "c") CUDA_TRY(h, cudaMemcpyAsync(dst, h->dev.u + NM, NM * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+            else { rc = cgb_salt_diag_to(h, names[v].c_str(), tsave[s], dst); if (rc) return rc; }
+        }
+        CUDA_TRY(h, cudaEventRecord(h->stage_ready[b], h->stream));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->stage_ready[b], 0));
+        CUDA_TRY(h, cudaMemcpyAsync(out + (size_t)s * per_save, h->d_stage[b], per_save * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+        CUDA_TRY(h, cudaEventRecord(h->stage_free[b], h->copy_stream));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    return CGB_OK;
+}
+
 extern "C" int cgb_solve_saveat(cgb_handle* h, const double* tsave, int64_t nsave, const char* vars, double* out)
 {
     if (!h || !tsave || !vars || !out || nsave < 1) return CGB_ERR_INVALID;
     clear_stale_error("cgb_solve_saveat");
     if (!h->have_state) CGB_FAIL(h, CGB_ERR_INVALID, "cgb_set_state has not been called");
-    if (h->cfg.physics == CGB_PHYSICS_HEAT_SALT) CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "cgb_solve_saveat: heat+salt uses cgb_advance_to + cgb_get_state");
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     int rc = finalize(h);
     if (rc) return rc;
+    if (h->cfg.physics == CGB_PHYSICS_HEAT_SALT) return salt_solve_saveat(h, tsave, nsave, vars, out);
     SaveVars sv;
     rc = parse_savevars(h, vars, sv);
     if (rc) return rc;

@@ -134,10 +134,11 @@ struct SfccFast {
 
 // heat+salt extras (Physics/Salt)
 struct SaltDev {
-    const double* por_cell;   // [N] porosity profile (SedimentCompactionInitializer), shared by all columns
+    const double* por_cell;   // porosity profile (SedimentCompactionInitializer): [N] shared by all columns, or [N*M] (por_per_column)
+    int por_per_column, _pad;
     const double* benthic;    // [M] SaltGradient.benthicSalt
-    double sat, org, para_por;
-    double alpha, n, theta_res, Tm;
+    const double *sat, *org, *alpha, *n, *theta_res, *Tm;   // [M] soil / DallAmicoSalt parameters of every column
+    double para_por;
     double tau, ds0, dc_max, courant, heat_courant;
     int surface_state;
 };

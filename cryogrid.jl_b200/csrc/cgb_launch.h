@@ -15,6 +15,7 @@ int cgb_launch_lite_warp_multi(cgb_handle* h, const double* targets, int n, doub
 int cgb_salt_finalize(cgb_handle* h, const std::vector<double>& zc);                               // cgb_tu_salt.cu
 int cgb_salt_launch(cgb_handle* h, double t_target, bool diag, const cgb::Diag& D, void* salt_diag);
 int cgb_salt_get_diag(cgb_handle* h, const char* var, double t, double* out);
+int cgb_salt_diag_to(cgb_handle* h, const char* var, double t, double* dev_out);   // cell variables only: N*M doubles
 int cgb_sfcc_fast_prepare(cgb_handle* h);                                                          // cgb_tu_sfcc_fast.cu (called by finalize)
 int cgb_launch_sfcc_fast_multi(cgb_handle* h, const double* targets, int n, double* saveT, double* saveW, long long save_stride);
 int cgb_sfcc_fast_selftest(cgb_handle* h, const double* T, long long n, double* out);

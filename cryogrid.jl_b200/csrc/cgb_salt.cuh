@@ -41,28 +41,10 @@ __global__ void __launch_bounds__(128) k_salt_euler(const __grid_constant__ Dev 
     }
     __syncthreads();
     const int jb = (N - 1) - lane * CPL;
-    const double m = 1.0 - 1.0 / S.n;
-    const double TmK0 = S.Tm + 273.15;
     const double Lf = P.Lsl * P.rho_w;
-    const double dTm_dc = TmK0 / Lf * (-P.R * TmK0);
     // warp-uniform quotients hoisted out of the step loop; the per-cell divisions below go through rcp_fast (correctly
     // rounded reciprocal, then one multiply: <= 1.5 ulp from the IEEE quotient)
-    const double q0 = TmK0 / Lf, gl = P.g / P.Lsl, Lg = P.Lsl / P.g, inv_tau = 1.0 / S.tau;
-    // static per-cell constants (porosity profile is shared by all columns)
-    double por[CPL], psi0[CPL], thwi[CPL], Cb[CPL], Kb[CPL];
-    {
-        double thm = (1.0 - S.para_por) * (1.0 - S.org), tho = (1.0 - S.para_por) * S.org;   // mineral()/organic() use para.por
-#pragma unroll
-        for (int j = 0; j < CPL; ++j) {
-            int i = lane * CPL + j;
-            por[j] = S.por_cell[i < N ? i : N - 1];
-            thwi[j] = por[j] * S.sat;
-            double tha = 1.0 - thwi[j] - thm - tho;
-            psi0[j] = vg_psi(S.sat * por[j], fmax(S.sat * por[j], por[j]), S.theta_res, S.alpha, S.n);
-            Cb[j] = P.ch_i * thwi[j] + P.ch_a * tha + P.ch_m * thm + P.ch_o * tho;
-            Kb[j] = P.sk_i * thwi[j] + P.sk_a * tha + P.sk_m * thm + P.sk_o * tho;
-        }
-    }
+    const double gl = P.g / P.Lsl, Lg = P.Lsl / P.g, inv_tau = 1.0 / S.tau;
     const double dC = P.ch_w - P.ch_i, dK = P.sk_w - P.sk_i;
 
     for (;;) {
@@ -71,6 +53,27 @@ __global__ void __launch_bounds__(128) k_salt_euler(const __grid_constant__ Dev 
         cu = __shfl_sync(FULL, cu, 0);
         if (cu >= (unsigned long long)M) break;
         const long long col = (long long)cu;
+        // per-column soil / curve parameters and the per-cell constants derived from them (once per column)
+        const double Ssat = S.sat[col], Sorg = S.org[col], Salpha = S.alpha[col], Sn = S.n[col], Sthres = S.theta_res[col];
+        const double m = 1.0 - 1.0 / Sn;
+        const double TmK0 = S.Tm[col] + 273.15;
+        const double dTm_dc = TmK0 / Lf * (-P.R * TmK0);
+        const double q0 = TmK0 / Lf;
+        double por[CPL], psi0[CPL], thwi[CPL], Cb[CPL], Kb[CPL];
+        {
+            double thm = (1.0 - S.para_por) * (1.0 - Sorg), tho = (1.0 - S.para_por) * Sorg;   // mineral()/organic() use para.por
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                int i = lane * CPL + j;
+                int ic = i < N ? i : N - 1;
+                por[j] = S.por_per_column ? S.por_cell[(size_t)ic * M + col] : S.por_cell[ic];
+                thwi[j] = por[j] * Ssat;
+                double tha = 1.0 - thwi[j] - thm - tho;
+                psi0[j] = vg_psi(Ssat * por[j], fmax(Ssat * por[j], por[j]), Sthres, Salpha, Sn);
+                Cb[j] = P.ch_i * thwi[j] + P.ch_a * tha + P.ch_m * thm + P.ch_o * tho;
+                Kb[j] = P.sk_i * thwi[j] + P.sk_a * tha + P.sk_m * thm + P.sk_o * tho;
+            }
+        }
         double T[CPL], c[CPL];
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
@@ -81,12 +84,17 @@ __global__ void __launch_bounds__(128) k_salt_euler(const __grid_constant__ Dev 
         double t = DIAG ? t_target : P.t[col];
         double dt = P.dt[col];
         const double benthic = S.benthic[col];
-        const double vtop = P.top.value + P.top_offset[col];
+        const double toff = P.top_offset[col];
         const double vbot = P.bot_value ? P.bot_value[col] : P.bot.value;
         int status = 0;
+        ForcingCursor ctop;
+        if (P.top.kind == 2) forcing_seek(P.top, ctop, fmin(fmax(t, __ldg(P.top.t)), __ldg(P.top.t + P.top.n - 1)));
         long long nsteps = 0;
 
         while (DIAG || t < t_target) {
+            // upper boundary temperature at the START of the step (ConstantTemperature, or a TemperatureBC with Input / PeriodicBC)
+            const double vtop = forcing_eval(P.top, ctop, t, status) + toff;
+            if (!DIAG && (status & 4)) break;
             double thw[CPL], dthT[CPL], dthc[CPL], Cc[CPL], dHdT[CPL], kc[CPL], dsm[CPL];
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
@@ -105,8 +113,8 @@ __global__ void __launch_bounds__(128) k_salt_euler(const __grid_constant__ Dev 
                     dpsi_dc = Lg * (-TK * (rT * rT)) * dTstar_dc;
                 } else { psi = psi0[j]; dpsi_dT = 0.0; dpsi_dc = 0.0; }
                 double dth;
-                double thsat = sel_max(S.sat * por[j], por[j]);
-                thw[j] = vg_theta(psi, thsat, S.theta_res, S.alpha, S.n, m, dth);
+                double thsat = sel_max(Ssat * por[j], por[j]);
+                thw[j] = vg_theta(psi, thsat, Sthres, Salpha, Sn, m, dth);
                 dthT[j] = dth * dpsi_dT;
                 dthc[j] = dth * dpsi_dc;
                 Cc[j] = fma(dC, thw[j], Cb[j]);
@@ -239,23 +247,30 @@ static int salt_finalize(cgb_handle* h, const std::vector<double>&)
     if (h->cfg.stepper != CGB_STEPPER_EULER) CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "heat+salt supports CGEuler only (as the reference)");
     SaltDev& s = h->salt;
     ParamArray& por = h->params["por"];
-    std::vector<double> pc(h->N);
-    for (int i = 0; i < h->N; ++i) pc[i] = (por.per == CGB_PER_CELL) ? por.v[i] : por.v[0];
+    const size_t M = (size_t)h->M;
+    s.por_per_column = (por.per == CGB_PER_CELL_COLUMN);
+    std::vector<double> pc(s.por_per_column ? (size_t)h->N * M : (size_t)h->N);
+    if (s.por_per_column) pc = por.v;
+    else for (int i = 0; i < h->N; ++i) pc[i] = (por.per == CGB_PER_CELL) ? por.v[i] : por.v[0];
     double* p_por; int rc = dev_upload(h, &p_por, pc); if (rc) return rc;
     s.por_cell = p_por;
-    ParamArray& b = h->params["benthic_salt"];
-    std::vector<double> bc((size_t)h->M);
-    for (long long c = 0; c < h->M; ++c) bc[c] = (b.per == CGB_PER_COLUMN) ? b.v[c] : b.v[0];
-    double* p_b; rc = dev_upload(h, &p_b, bc); if (rc) return rc;
-    s.benthic = p_b;
+    auto per_column = [&](const char* name, const double** dst) {
+        ParamArray& a = h->params[name];
+        std::vector<double> v(M);
+        for (size_t c = 0; c < M; ++c) v[c] = (a.per == CGB_PER_COLUMN) ? a.v[c] : a.v[0];
+        double* p; int r = dev_upload(h, &p, v); *dst = p; return r;
+    };
+    rc |= per_column("benthic_salt", &s.benthic);
+    rc |= per_column("sat", &s.sat); rc |= per_column("org", &s.org); rc |= per_column("vg_alpha", &s.alpha); rc |= per_column("vg_n", &s.n);
+    rc |= per_column("theta_res", &s.theta_res); rc |= per_column("Tm", &s.Tm);
+    if (rc) return rc;
     auto G = [&](const char* n) { return h->params[n].v[0]; };
-    s.sat = G("sat"); s.org = G("org"); s.para_por = G("salt_para_por");
-    s.alpha = G("vg_alpha"); s.n = G("vg_n"); s.theta_res = G("theta_res"); s.Tm = G("Tm");
+    s.para_por = G("salt_para_por");
     s.tau = G("tau"); s.ds0 = G("ds0"); s.dc_max = G("salt_dc_max");
     s.courant = h->cfg.courant; s.heat_courant = 0.5;                 // salt_types.jl:13 ; heat_types.jl:17
     s.surface_state = (int)G("salt_surface_state");
-    if (h->forc[0].kind != 0 || (h->forc[1].kind != 0 && !h->params.count("bot_value")))
-        CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "heat+salt supports constant boundary values (ConstantTemperature / GeothermalHeatFlux)");
+    if (h->forc[1].kind != 0 && !h->params.count("bot_value"))
+        CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "heat+salt supports a constant lower boundary value (GeothermalHeatFlux)");
     if (h->cfg.top_kind != CGB_BC_DIRICHLET || h->cfg.bot_kind != CGB_BC_NEUMANN)
         CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "heat+salt supports a Dirichlet top and Neumann bottom (examples/heat_sfcc_salt_constantbc.jl)");
     return CGB_OK;
@@ -296,11 +311,12 @@ static int salt_launch(cgb_handle* h, double t_target, bool diag, const cgb::Dia
     return salt_launch_c<false>(h, t_target, D);
 }
 
-static int salt_get_diag(cgb_handle* h, const char* var, double t, double* out)
+// one diagnostic variable evaluated at the current state and time t, written to a DEVICE buffer (dev_out: N*M or (N+1)*M doubles)
+static int salt_diag_to(cgb_handle* h, const char* var, double t, double* dev_out, size_t* count)
 {
     using namespace cgb;
     SaltDiag D{};
-    double* s = h->d_scratch;
+    double* s = dev_out;
     size_t NM = (size_t)h->N * h->M, cnt = NM;
     std::string v(var);
     if (v == "thw") D.thw = s; else if (v == "dthwdT") D.dthwdT = s; else if (v == "dthwdc") D.dthwdc = s; else if (v == "C") D.C = s;
@@ -309,10 +325,17 @@ static int salt_get_diag(cgb_handle* h, const char* var, double t, double* out)
     else if (v == "k") { D.k = s; cnt = NM + h->M; } else if (v == "ds") { D.ds = s; cnt = NM + h->M; }
     else if (v == "jH") { D.jH = s; cnt = NM + h->M; } else if (v == "jc") { D.jc = s; cnt = NM + h->M; }
     else CGB_FAIL(h, CGB_ERR_INVALID, "unknown heat+salt diagnostic '%s'", var);
+    if (count) *count = cnt;
     Diag dummy{};
-    int rc = salt_launch(h, t, true, dummy, &D);
+    return salt_launch(h, t, true, dummy, &D);
+}
+
+static int salt_get_diag(cgb_handle* h, const char* var, double t, double* out)
+{
+    size_t cnt = 0;
+    int rc = salt_diag_to(h, var, t, h->d_scratch, &cnt);
     if (rc) return rc;
-    CUDA_TRY(h, cudaMemcpyAsync(out, s, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(out, h->d_scratch, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return CGB_OK;
 }

@@ -48,21 +48,44 @@ def compaction(grid: Grid, porosityZero=0.4, porosityMin=0.03):
 
 
 class SalineTile:
-    """M saline-sediment columns: one SalineGround layer, SaltHeatBC(SaltGradient, ConstantTemperature) on top,
-    GeothermalHeatFlux at the bottom; per-column benthic salt concentration."""
+    """M saline-sediment columns: one SalineGround layer, SaltHeatBC(SaltGradient, upper temperature) on top, GeothermalHeatFlux at
+    the bottom.  Every numeric parameter may be a scalar or an array of length `ncolumns` (ensemble members): benthic salt
+    concentration, saturation, organic fraction, van Genuchten alpha / n, porosityZero of the compaction initializer.  The upper
+    temperature is a constant (ConstantTemperature), a PeriodicBC or a forcing table ("table", ts, ys)."""
 
     def __init__(self, grid=DefaultGrid_10cm, sfcc=None, sat=1.0, org=0.0, T_ub=0.0, salt_bc=None, Qgeo=0.053,
                  salt=None, porinit=None, T0=-2.0, c0=0.0, ncolumns=1, prop=None):
         self.grid, self.M = grid, int(ncolumns)
+        M = self.M
         self.sfcc = sfcc or DallAmicoSalt(swrc=VanGenuchten(alpha=4.06, n=2.03))
-        self.sat, self.org, self.T_ub, self.Qgeo = float(sat), float(org), float(T_ub), float(Qgeo)
+        self.sat_c, self.org_c = _col(sat, M), _col(org, M)
+        self.alpha_c, self.n_c = _col(self.sfcc.swrc.alpha, M), _col(self.sfcc.swrc.n, M)
+        self.thres_c, self.Tm_c = _col(self.sfcc.swrc.theta_res, M), _col(self.sfcc.Tm, M)
+        self.Qgeo = float(Qgeo)
+        if isinstance(T_ub, tuple):
+            self.top_forcing, self.T_ub = T_ub, 0.0
+        elif hasattr(T_ub, "period"):       # PeriodicBC
+            self.top_forcing, self.T_ub = ("periodic", T_ub.period, T_ub.amplitude, T_ub.phaseshift, T_ub.level), 0.0
+        else:
+            self.top_forcing, self.T_ub = ("constant", float(T_ub)), float(T_ub)
         self.salt_bc = salt_bc or SaltGradient()
         self.salt = salt or SaltMassBalance()
         self.tp = prop or ThermalProperties()
         pi = porinit or SedimentCompactionInitializer()
-        self.por_cell = compaction(grid, pi.porosityZero, pi.porosityMin)
+        p0 = _col(pi.porosityZero, M)
+        self.por_per_column = bool(np.ptp(p0) > 0)
+        self.por_cm = np.stack([compaction(grid, float(p0[c]), pi.porosityMin) for c in range(M)], axis=1) if self.por_per_column else None
+        self.por_cell = compaction(grid, float(p0[0]), pi.porosityMin)
         self.benthic = _col(self.salt_bc.benthicSalt, self.M)
         self.T0, self.c0 = T0, c0
+        self.per_column_soil = any(np.ptp(a) > 0 for a in (self.sat_c, self.org_c, self.alpha_c, self.n_c, self.thres_c, self.Tm_c))
+
+    # scalar views of column 0 (single-class tiles)
+    sat = property(lambda self: float(self.sat_c[0]))
+    org = property(lambda self: float(self.org_c[0]))
+
+    def por_of(self, c):
+        return self.por_cm[:, c] if self.por_per_column else self.por_cell
 
     def initialcondition(self):
         N, M = self.grid.ncells, self.M
@@ -90,10 +113,17 @@ class SaltEngine(_EngineBase):
         self.h = h
         e = L.as_f64(tile.grid.edges)
         self._check(self.lib.cgb_set_grid(self.h, L.dptr(e)))
-        self._param("por", tile.por_cell, L.PER_CELL)
-        for name, v in (("sat", tile.sat), ("org", tile.org), ("vg_alpha", tile.sfcc.swrc.alpha), ("vg_n", tile.sfcc.swrc.n),
-                        ("theta_res", tile.sfcc.swrc.theta_res), ("Tm", tile.sfcc.Tm), ("tau", tile.salt.prop.tau),
-                        ("ds0", tile.salt.prop.ds0), ("salt_dc_max", tile.salt.dc_max),
+        if tile.por_per_column:
+            self._param("por", np.ascontiguousarray(tile.por_cm[:, cols]), L.PER_CELL_COLUMN)
+        else:
+            self._param("por", tile.por_cell, L.PER_CELL)
+        for name, arr in (("sat", tile.sat_c), ("org", tile.org_c), ("vg_alpha", tile.alpha_c), ("vg_n", tile.n_c),
+                          ("theta_res", tile.thres_c), ("Tm", tile.Tm_c)):
+            if np.ptp(arr) > 0:
+                self._param(name, arr[cols], L.PER_COLUMN)
+            else:
+                self._param(name, [float(arr[0])], L.PER_GLOBAL)
+        for name, v in (("tau", tile.salt.prop.tau), ("ds0", tile.salt.prop.ds0), ("salt_dc_max", tile.salt.dc_max),
                         ("salt_surface_state", float(tile.salt_bc.surfaceState))):
             self._param(name, [float(v)], L.PER_GLOBAL)
         for k, v in tile.tp.as_dict().items():
@@ -101,7 +131,14 @@ class SaltEngine(_EngineBase):
         self._param("benthic_salt", tile.benthic[cols], L.PER_COLUMN)
         self._param("bot_value", np.full(self.M, -tile.Qgeo), L.PER_COLUMN)
         self._check(self.lib.cgb_set_freezecurve(self.h, 0, L.FC_DALLAMICOSALT, L.SOLVER_NEWTON))
-        self._check(self.lib.cgb_set_forcing_constant(self.h, L.TOP, tile.T_ub))
+        f = tile.top_forcing
+        if f[0] == "table":
+            ts, ys = L.as_f64(f[1]), L.as_f64(f[2])
+            self._check(self.lib.cgb_set_forcing_table(self.h, L.TOP, L.dptr(ts), L.dptr(ys), ts.size))
+        elif f[0] == "periodic":
+            self._check(self.lib.cgb_set_forcing_periodic(self.h, L.TOP, *[float(x) for x in f[1:]]))
+        else:
+            self._check(self.lib.cgb_set_forcing_constant(self.h, L.TOP, tile.T_ub))
 
     def set_state(self, u, t0):
         u = L.as_f64(u)
@@ -122,6 +159,13 @@ class SaltEngine(_EngineBase):
         du = np.empty((2, self.N, self.M))
         self._check(self.lib.cgb_rhs(self.h, float(t), L.dptr(du)))
         return du
+
+    def solve_saveat(self, tsave, savevars=("T", "c", "thw")):
+        """out[nsave, nvars, N, M]: the prognostic T, c and cell diagnostics (thw, C, dHdT, kc, H, dT, dc ...) at every save time."""
+        tsave = L.as_f64(tsave)
+        out = np.empty((tsave.size, len(savevars), self.N, self.M))
+        self._check(self.lib.cgb_solve_saveat(self.h, L.dptr(tsave), tsave.size, ",".join(savevars).encode(), L.dptr(out)))
+        return out
 
     def diag(self, var, t):
         n = self.N + 1 if var in ("k", "jH", "ds", "jc") else self.N

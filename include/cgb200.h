@@ -71,7 +71,8 @@ extern "C" {
 #define CGB_PER_LAYER        1       /* n_layers values */
 #define CGB_PER_COLUMN       2       /* M values */
 #define CGB_PER_COLUMN_LAYER 3       /* n_layers*M values, p[layer*M + col] */
-#define CGB_PER_CELL         4       /* N values (heat+salt porosity profile) */
+#define CGB_PER_CELL         4       /* N values (heat+salt porosity profile shared by all columns) */
+#define CGB_PER_CELL_COLUMN  5       /* N*M values, p[cell*M + col] (heat+salt porosity profile of every column) */
 
 /* per-column status bits (cgb_get_status) */
 #define CGB_STATUS_MAXITERS      1   /* LiteImplicit hit maxiters: cglite_step.jl:74-77 (ReturnCode.MaxIters) */

@@ -745,9 +745,12 @@ void cg_compaction(const double* edges, int n, double por0, double por_min, doub
 
 /* Salt/salt_diffusion.jl:3-30 (freezethaw!), :51-78 (computediagnostic!), salt_bc.jl:18-31 and
  * heat_bc.jl:9-35 (interact!), salt_diffusion.jl:124-165 (computeprognostic!). */
-void cg_salt_rhs(const cg_salt_column* col, const double* T, const double* c, cg_salt_work* w)
+void cg_salt_rhs(const cg_salt_column* col, const double* T, const double* c, cg_salt_work* w) { cg_salt_rhs_t(col, T, c, 0.0, w); }
+
+int cg_salt_rhs_t(const cg_salt_column* col, const double* T, const double* c, double t, cg_salt_work* w)
 {
-    int n = col->n;
+    int n = col->n, status = 0;
+    const double T_ub = col->use_top_forcing ? cg_forcing_eval(&col->top, t, &status) : col->T_ub;
     const cg_thermal* tp = &col->tp;
     cg_grid(col->edges, n + 1, w->zc, w->dk, w->dxc);
     /* SimpleSoil defaults of the parameterisation (Soils/para/simple.jl:9): mineral()/organic() use
@@ -775,7 +778,7 @@ void cg_salt_rhs(const cg_salt_column* col, const double* T, const double* c, cg
     for (int i = 0; i < n; ++i) { w->dH[i] = 0.0; w->dc_F[i] = 0.0; }
     for (int i = 0; i <= n; ++i) { w->jH[i] = 0.0; w->jc[i] = 0.0; }
     /* boundaries */
-    w->jH[0] += cg_flux(col->T_ub, T[0], w->dk[0] / 2.0, w->k[0]);
+    w->jH[0] += cg_flux(T_ub, T[0], w->dk[0] / 2.0, w->k[0]);
     w->jc[0] = (col->surface_state == 0) ? -w->ds[0] * (c[0] - col->benthic_salt) / (w->dk[0] / 2.0) : 0.0;
     w->jH[n] += col->bot_value;
     cg_nonlineardiffusion(w->dH, w->jH, T, w->dxc, w->k, w->dk, n);
@@ -790,6 +793,7 @@ void cg_salt_rhs(const cg_salt_column* col, const double* T, const double* c, cg
         w->dT[i] = (-B * G + D * E) / (A * E - B * F);
         w->dc[i] = (-F * D + A * G) / (A * E - B * F);
     }
+    return status;
 }
 
 /* salt_diffusion.jl:107-122 (salt CFL + MaxDelta) and heat_conduction.jl:162-182 (heat CFL). */
@@ -816,7 +820,7 @@ int cg_salt_advance_trace(const cg_salt_column* col, double* T, double* c, doubl
     int status = 0, n = col->n;
     int64_t k = 0;
     while (*t < t_target) {
-        cg_salt_rhs(col, T, c, w);
+        status |= cg_salt_rhs_t(col, T, c, *t, w);
         for (int i = 0; i < n; ++i) { T[i] += (*dt) * w->dT[i]; c[i] += (*dt) * w->dc[i]; }
         if (dt_trace && k < cap) dt_trace[k] = *dt;
         ++k;

@@ -189,6 +189,9 @@ typedef struct {
     double bot_value;        /* -Qgeo */
     double courant, dc_max;  /* CFL(0.5, MaxDelta(5e-3)), salt_types.jl:13 */
     double heat_courant;     /* heat CFL(0.5, MaxDelta(Inf)), heat_types.jl:17 */
+    int32_t use_top_forcing; /* 1: the upper boundary temperature is top(t) (TemperatureBC with an Input / PeriodicBC), else T_ub */
+    int32_t _pad;
+    cg_forcing top;
 } cg_salt_column;
 
 typedef struct {
@@ -200,6 +203,7 @@ typedef struct {
 
 void   cg_compaction(const double* edges, int n, double por0, double por_min, double* por);
 void   cg_salt_rhs(const cg_salt_column* col, const double* T, const double* c, cg_salt_work* w);
+int    cg_salt_rhs_t(const cg_salt_column* col, const double* T, const double* c, double t, cg_salt_work* w);
 double cg_salt_timestep(const cg_salt_column* col, const cg_salt_work* w);
 int    cg_salt_advance(const cg_salt_column* col, double* T, double* c, double* t, double* dt, double t_target,
                        double dtmin, double dtmax, int64_t* nsteps, cg_salt_work* w);

@@ -50,7 +50,7 @@ class SaltColumn(C.Structure):
     _fields_ = [("n", C.c_int32), ("surface_state", C.c_int32), ("edges", _D), ("por", _D), ("sat", C.c_double), ("org", C.c_double),
                 ("fc", FreezeCurve), ("tp", Thermal), ("tau", C.c_double), ("ds0", C.c_double), ("T_ub", C.c_double),
                 ("benthic_salt", C.c_double), ("bot_value", C.c_double), ("courant", C.c_double), ("dc_max", C.c_double),
-                ("heat_courant", C.c_double)]
+                ("heat_courant", C.c_double), ("use_top_forcing", C.c_int32), ("_pad", C.c_int32), ("top", Forcing)]
 
 
 class SaltWork(C.Structure):
@@ -123,6 +123,7 @@ def lib():
         l.cg_steadystate_init.argtypes = [C.POINTER(Column), C.c_double, C.c_double, C.c_int, C.c_double, _D, C.POINTER(Work)]
         l.cg_compaction.argtypes = [_D, C.c_int, C.c_double, C.c_double, _D]
         l.cg_salt_rhs.argtypes = [C.POINTER(SaltColumn), _D, _D, C.POINTER(SaltWork)]
+        l.cg_salt_rhs_t.restype = C.c_int; l.cg_salt_rhs_t.argtypes = [C.POINTER(SaltColumn), _D, _D, C.c_double, C.POINTER(SaltWork)]
         l.cg_salt_timestep.restype = C.c_double; l.cg_salt_timestep.argtypes = [C.POINTER(SaltColumn), C.POINTER(SaltWork)]
         l.cg_salt_advance.restype = C.c_int
         l.cg_salt_advance.argtypes = [C.POINTER(SaltColumn), _D, _D, _D, _D, C.c_double, C.c_double, C.c_double, _I64, C.POINTER(SaltWork)]
@@ -307,13 +308,16 @@ class OracleSaltColumn:
         self.tile = tile
         n = tile.grid.ncells
         self.n = n
-        self.edges = f64(tile.grid.edges); self.por = f64(tile.por_cell)
-        d = dict(kind=3, alpha=float(tile.sfcc.swrc.alpha), n=float(tile.sfcc.swrc.n), theta_res=float(tile.sfcc.swrc.theta_res),
-                 Tm=float(tile.sfcc.Tm), beta=1.0, omega=1.0)
+        self.edges = f64(tile.grid.edges); self.por = f64(tile.por_of(c))
+        d = dict(kind=3, alpha=float(tile.alpha_c[c]), n=float(tile.n_c[c]), theta_res=float(tile.thres_c[c]),
+                 Tm=float(tile.Tm_c[c]), beta=1.0, omega=1.0)
+        self.keep = []
+        top = forcing_struct(tile.top_forcing, self.keep)
         self.col = SaltColumn(n=n, surface_state=int(tile.salt_bc.surfaceState), edges=dp(self.edges), por=dp(self.por),
-                              sat=tile.sat, org=tile.org, fc=fc_struct(d, solver=1), tp=thermal_struct(tile.tp),
+                              sat=float(tile.sat_c[c]), org=float(tile.org_c[c]), fc=fc_struct(d, solver=1), tp=thermal_struct(tile.tp),
                               tau=tile.salt.prop.tau, ds0=tile.salt.prop.ds0, T_ub=tile.T_ub, benthic_salt=float(tile.benthic[c]),
-                              bot_value=-tile.Qgeo, courant=tile.salt.courant_number, dc_max=tile.salt.dc_max, heat_courant=0.5)
+                              bot_value=-tile.Qgeo, courant=tile.salt.courant_number, dc_max=tile.salt.dc_max, heat_courant=0.5,
+                              use_top_forcing=int(tile.top_forcing[0] != "constant"), top=top)
         self.arrays = {}
         self.w = SaltWork()
         for name in SaltWork._names:
@@ -325,9 +329,9 @@ class OracleSaltColumn:
         m = self.n + 1 if name in ("k", "ds", "jH", "jc") else self.n
         return self.arrays[name][:m].copy()
 
-    def rhs(self, T, c):
+    def rhs(self, T, c, t=0.0):
         T, c = f64(T), f64(c)
-        lib().cg_salt_rhs(C.byref(self.col), dp(T), dp(c), C.byref(self.w))
+        lib().cg_salt_rhs_t(C.byref(self.col), dp(T), dp(c), float(t), C.byref(self.w))
         return self.get("dT"), self.get("dc")
 
     def timestep(self):

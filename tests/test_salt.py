@@ -99,3 +99,55 @@ def test_salt_mass_balance_large_batch():
     assert np.all(np.isfinite(u)) and u[1].min() > -1e-6 and np.all(u[1].max(axis=0) <= tile.benthic + 1e-6)
     assert np.all(u[1][0] > 0)
     eng.close()
+
+
+@pytest.mark.gpu
+def test_salt_per_column_parameters_forcing_and_saveat(orc):
+    # ensemble over soil parameters (saturation, organic fraction, van Genuchten alpha / n, porosityZero) and benthic salt, upper
+    # temperature from a forcing table (salt_diffusion.jl:107-165 with a TemperatureBC(Input) on top instead of ConstantTemperature)
+    import common
+    M = 10
+    rng = np.random.default_rng(8)
+    ts = 3600.0 * np.arange(0, 24 * 40 + 1)
+    Tub = -1.0 + 1.5 * np.sin(2 * np.pi * ts / (10 * 86400.0))
+    tile = cg.SalineTile(grid=cg.DefaultGrid_10cm, sfcc=cg.DallAmicoSalt(swrc=cg.VanGenuchten(alpha=rng.uniform(2.0, 5.0, M), n=rng.uniform(1.6, 2.4, M))),
+                         sat=rng.uniform(0.8, 1.0, M), org=rng.uniform(0.0, 0.2, M), T_ub=("table", ts, Tub),
+                         salt_bc=cg.SaltGradient(rng.uniform(600.0, 1000.0, M), 0),
+                         porinit=cg.SedimentCompactionInitializer(porosityZero=rng.uniform(0.35, 0.5, M)), ncolumns=M)
+    assert tile.per_column_soil and tile.por_per_column
+    u0 = tile.initialcondition()
+    u0[0] += rng.uniform(-2.0, 1.0, u0[0].shape); u0[1] += rng.uniform(0.0, 600.0, u0[1].shape)
+    eng = cg.SaltEngine(tile)
+    eng.set_state(u0, 0.0)
+    tq = 5 * 86400.0 + 1234.0
+    du = eng.rhs(tq)
+    dk = tile.grid.dedges
+    for c in range(M):
+        oc = orc.OracleSaltColumn(tile, c)
+        dT, dc = oc.rhs(u0[0, :, c], u0[1, :, c], tq)
+        sT = np.maximum(np.abs(dT), np.max(np.abs(oc.get("jH"))) / dk / oc.get("dHdT"))
+        sc = np.maximum(np.abs(dc), np.max(np.abs(oc.get("jc"))) / dk / np.maximum(oc.get("thw"), 1e-3))
+        assert np.max(np.abs(du[0, :, c] - dT) / sT) < 1e-10 and np.max(np.abs(du[1, :, c] - dc) / sc) < 1e-10, c
+    # saved outputs through cgb_solve_saveat (T, c prognostic; θw, C diagnostics at the saved state) vs the oracle
+    tsave = 86400.0 * np.array([0.5, 1.0, 3.0])
+    out = eng.solve_saveat(tsave, ("T", "c", "thw", "C"))
+    st, steps = eng.status()
+    assert not st.any()
+    for c in (0, 4, 9):
+        oc = orc.OracleSaltColumn(tile, c)
+        T, cc, tr, dtr, ns = u0[0, :, c], u0[1, :, c], 0.0, 60.0, 0
+        for k, tt in enumerate(tsave):
+            T, cc, tr, dtr, n2, s2 = oc.advance(T, cc, tr, dtr, tt)
+            ns += n2
+            assert s2 == 0
+            oc.rhs(T, cc, tt)
+            assert np.max(np.abs(out[k, 0, :, c] - T)) <= 1e-9 and np.max(np.abs(out[k, 1, :, c] - cc)) <= 1e-9 * max(1.0, np.max(np.abs(cc)))
+            np.testing.assert_allclose(out[k, 2, :, c], oc.get("thw"), rtol=1e-9, atol=1e-12)
+            np.testing.assert_allclose(out[k, 3, :, c], oc.get("C"), rtol=1e-9)
+        assert steps[c] == ns
+    # a forcing table that ends before the target: FORCING_RANGE status (Interpolated1D BoundsError), like the heat path
+    eng.set_state(u0, 39.9 * 86400.0)
+    eng.advance_to(41 * 86400.0)
+    st, _ = eng.status()
+    assert np.all(st & 4)
+    eng.close()
