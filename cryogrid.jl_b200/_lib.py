@@ -88,6 +88,7 @@ SIGNATURES = {
     "cgb_selftest_rcp": (C.c_int, [_D, C.c_int64, _D, _D, _D]),
     "cgb_selftest_sfcc_curve": (C.c_int, [_P, _D, C.c_int64, _D]),
     "cgb_selftest_explog": (C.c_int, [_D, C.c_int64, _D, _D]),
+    "cgb_selftest_explog_tab": (C.c_int, [_D, C.c_int64, _D, _D]),
 }
 
 _lib = None

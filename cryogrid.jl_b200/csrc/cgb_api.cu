@@ -1274,13 +1274,21 @@ extern "C" int cgb_selftest_sfcc_curve(cgb_handle* h, const double* T, int64_t n
 }
 
 // self-test of the transcendental replacements used by the van Genuchten powers (tests/test_gpu_sfcc.py)
-__global__ void k_selftest_explog(const double* __restrict__ x, long long n, double* ex, double* lg)
+__global__ void k_selftest_explog(const double* __restrict__ x, long long n, double* ex, double* lg, int tab)
 {
+    vgtab_init();
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i < n) { ex[i] = exp_fast(x[i]); lg[i] = log_pos(fabs(x[i])); }
+    if (i < n) {
+        if (tab) { ex[i] = exp_tab(x[i]); lg[i] = log_tab(fabs(x[i])); }
+        else { ex[i] = exp_fast(x[i]); lg[i] = log_pos(fabs(x[i])); }
+    }
 }
 
-extern "C" int cgb_selftest_explog(const double* x, int64_t n, double* out_exp, double* out_log)
+static int selftest_explog(const double* x, int64_t n, double* out_exp, double* out_log, int tab);
+extern "C" int cgb_selftest_explog(const double* x, int64_t n, double* out_exp, double* out_log) { return selftest_explog(x, n, out_exp, out_log, 0); }
+// the table-driven variants used by the stepping kernels (exp_tab / log_tab, csrc/cgb_common.cuh)
+extern "C" int cgb_selftest_explog_tab(const double* x, int64_t n, double* out_exp, double* out_log) { return selftest_explog(x, n, out_exp, out_log, 1); }
+static int selftest_explog(const double* x, int64_t n, double* out_exp, double* out_log, int tab)
 {
     if (!x || n < 1 || !out_exp || !out_log) return CGB_ERR_INVALID;
     int ndev = 0;
@@ -1288,7 +1296,7 @@ extern "C" int cgb_selftest_explog(const double* x, int64_t n, double* out_exp, 
     double* d = nullptr;
     if (cudaMalloc((void**)&d, 3 * n * sizeof(double)) != cudaSuccess) return CGB_ERR_ALLOC;
     cudaMemcpy(d, x, n * sizeof(double), cudaMemcpyHostToDevice);
-    k_selftest_explog<<<(unsigned)((n + 255) / 256), 256>>>(d, n, d + n, d + 2 * n);
+    k_selftest_explog<<<(unsigned)((n + 255) / 256), 256>>>(d, n, d + n, d + 2 * n, tab);
     cudaError_t e = cudaDeviceSynchronize();
     cudaMemcpy(out_exp, d + n, n * sizeof(double), cudaMemcpyDeviceToHost);
     cudaMemcpy(out_log, d + 2 * n, n * sizeof(double), cudaMemcpyDeviceToHost);

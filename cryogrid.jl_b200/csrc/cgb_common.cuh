@@ -327,23 +327,86 @@ __device__ __forceinline__ double lut_eval_bucket(const double* __restrict__ Hk,
     return fma(H - __ldg(Hk + lo), __ldg(Sk + lo), __ldg(Tk + lo));
 }
 
-// x^n and (1+x^n)^-m for x > 0 through exp_fast / log_pos (~150 instructions).  Inlined everywhere: with the library
-// exp/log/log1p (~520 instructions) this had to stay out of line (the unrolled callers overflowed the instruction cache); with
-// the lean versions inlining measured +9 % on the Newton kernel and +5 % on heat+salt.
+// ---- table-driven exp / log for the van Genuchten powers of the STEPPING kernels ------------------------------------------
+// 64-entry tables in (static) shared memory, filled by vgtab_init() at kernel start: {1/c_i, log c_i} for c_i = 1 + (i + 1/2)/64
+// and 2^(j/64).  log x = e ln2 + log c_i + log1p(m/c_i - 1) with |m/c_i - 1| <= 2^-7 (degree-6 series), exp a = 2^(k/64) e^r with
+// |r| <= ln2/128 (degree-5 series): ~17 and ~14 instructions against ~35 and ~25 of log_pos / exp_fast, <= 3 ulp
+// (cgb_selftest_explog, tests/test_gpu_sfcc.py).  The diagnostics kernels keep the series versions.
+__shared__ double g_vgtab[192];
+
+__device__ __forceinline__ void vgtab_init()
+{
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+        const double c = 1.0 + (i + 0.5) / 64.0;
+        g_vgtab[2 * i] = 1.0 / c;
+        g_vgtab[2 * i + 1] = log(c);
+        g_vgtab[128 + i] = exp2(i / 64.0);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ double exp_tab(double a)
+{
+    a = sel_min(sel_max(a, -708.0), 709.0);
+    const double MAGIC = 6755399441055744.0;             // 1.5 * 2^52: round-to-nearest-integer by addition
+    const double t = fma(a, 92.332482616893656877, MAGIC);   // 64 / ln 2
+    const int k = __double2loint(t);
+    const double kd = t - MAGIC;
+    double r = fma(kd, -6.93147180369123816490e-01 / 64.0, a);       // ln2_hi / 64 (33 significant bits: kd * hi is exact)
+    r = fma(kd, -1.90821492927058770002e-10 / 64.0, r);
+    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = p * r;                                            // e^r - 1, |r| <= ln2 / 128 (truncation r^6/720 = 3.5e-17)
+    const double T = g_vgtab[128 + (k & 63)];
+    const double res = fma(T, p, T);
+    return __hiloint2double(__double2hiint(res) + ((k >> 6) << 20), __double2loint(res));
+}
+
+__device__ __forceinline__ double log_tab(double x)      // normal x > 0
+{
+    const int hi = __double2hiint(x), lo = __double2loint(x);
+    const int e = (hi >> 20) - 1023;
+    const int idx = (hi >> 14) & 63;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+    const double2 t = *reinterpret_cast<const double2*>(&g_vgtab[2 * idx]);     // 1/c, log c
+    const double r = fma(m, t.x, -1.0);                   // |r| <= 2^-7
+    double p = fma(r, -1.0 / 6.0, 0.2);
+    p = fma(p, r, -0.25);
+    p = fma(p, r, 1.0 / 3.0);
+    p = fma(p, r, -0.5);
+    p = p * r;
+    const double l1 = fma(p, r, r);                       // log1p(r), truncation r^7/7 = 2.5e-16
+    const double ed = (double)e;
+    return fma(ed, 6.93147180369123816490e-01, fma(ed, 1.90821492927058770002e-10, t.y + l1));
+}
+
+// x^n and (1+x^n)^-m for x > 0 through exp / log (~150 instructions with the series versions, ~75 with the tables).  Inlined
+// everywhere: with the library exp/log/log1p (~520 instructions) this had to stay out of line (the unrolled callers overflowed the
+// instruction cache); with the lean versions inlining measured +9 % on the Newton kernel and +5 % on heat+salt.
+template <bool TAB = false>
 __device__ __forceinline__ void vg_powers_body(double x, double n, double m, double& xn, double& pb)
 {
-    xn = exp_fast(n * log_pos(x));
-    pb = exp_fast(-m * log_pos(1.0 + xn));       // 1 + x^n rounds with absolute error 1.1e-16: relative 1e-16 m in pb
+    if (TAB) {
+        xn = exp_tab(n * log_tab(x));
+        pb = exp_tab(-m * log_tab(1.0 + xn));
+    } else {
+        xn = exp_fast(n * log_pos(x));
+        pb = exp_fast(-m * log_pos(1.0 + xn));   // 1 + x^n rounds with absolute error 1.1e-16: relative 1e-16 m in pb
+    }
 }
+template <bool TAB = false>
 __device__ __forceinline__ double2 vg_powers(double x, double n, double m)
 {
     double2 r;
-    vg_powers_body(x, n, m, r.x, r.y);
+    vg_powers_body<TAB>(x, n, m, r.x, r.y);
     return r;
 }
 
 // van Genuchten θ(ψ) and dθ/dψ for ψ <= 0; θsat for ψ > 0.  x^n and (1+x^n)^-m go through exp/log (x > 0, base >= 1:
 // no special cases needed), about half the cost of two pow() calls; error ~ (n |log x| + 2) ulp.
+template <bool TAB = false>
 __device__ __forceinline__ double vg_theta(double psi, double thsat, double thres, double alpha, double n, double m, double& dth)
 {
     if (psi <= 0.0) {
@@ -356,7 +419,7 @@ __device__ __forceinline__ double vg_theta(double psi, double thsat, double thre
             return fma(d, rs, thres);
         }
         if (x > 0.0) {
-            double2 r = vg_powers(x, n, m);
+            double2 r = vg_powers<TAB>(sel_max(x, 1e-300), n, m);
             double xn = r.x, pb = r.y;
             double base = 1.0 + xn;
             dth = d * m * n * alpha * (xn * rcp_fast(x)) * (pb * rcp_fast(base));
@@ -380,6 +443,7 @@ __device__ __forceinline__ double vg_psi(double th, double thsat, double thres, 
 }
 
 // SFCC θw(T) and dθw/dT from the staged layer constants (DallAmico / PainterKarra).
+template <bool TAB = false>
 __device__ __forceinline__ double sfcc_theta(const double* lc, double T, double& dthdT)
 {
     double TK = T + 273.15;
@@ -390,7 +454,7 @@ __device__ __forceinline__ double sfcc_theta(const double* lc, double T, double&
     double dth;
     double thtot = lc[LC_THWI];
     double thsat = fmax(thtot, lc[LC_POR]);
-    double thw = vg_theta(psi, thsat, lc[LC_THRES], lc[LC_ALPHA], lc[LC_N], lc[LC_M], dth);
+    double thw = vg_theta<TAB>(psi, thsat, lc[LC_THRES], lc[LC_ALPHA], lc[LC_N], lc[LC_M], dth);
     dthdT = dth * dpsi;
     return thw;
 }

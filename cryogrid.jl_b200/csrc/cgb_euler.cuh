@@ -109,7 +109,7 @@ __device__ __forceinline__ void sfcc_newton_solve(const double* lc, double L, do
     double lo = -273.0, hi = lc[LC_NW_TSTARC];
     if (!(T > lo && T < hi)) T = hi;                   // a cell that has just crossed the kink starts at it
     for (int it = 0; it < 200; ++it) {
-        thw = sfcc_theta(lc, T, dth);
+        thw = sfcc_theta<!EXACT>(lc, T, dth);
         C = fma(dC, thw, lc[LC_CBS]);
         double r = (T * C + L * thw) - H;
         dHdT = C + dth * (L + T * dC);                 // heat_methods.jl:105
@@ -127,7 +127,7 @@ __device__ __forceinline__ void sfcc_newton_solve(const double* lc, double L, do
         T = Tn;
         if (done) {
             if (EXACT) {
-                thw = sfcc_theta(lc, T, dth);
+                thw = sfcc_theta<!EXACT>(lc, T, dth);
                 C = fma(dC, thw, lc[LC_CBS]);
                 dHdT = C + dth * (L + T * dC);
             } else {
@@ -158,7 +158,7 @@ __device__ __forceinline__ void freezethaw_body(const Dev& P, const double* lc, 
     if (MODE == 5 || (MODE == 0 && P.tform)) {
         // temperature form (soil_heat.jl:100-113): H IS the temperature; θw, ∂θw∂T straight from the curve, the REGULAR heat capacity
         T = H;
-        thw = sfcc_theta(lc, T, dth);
+        thw = sfcc_theta<!EXACT>(lc, T, dth);
         C = fma(dC, thw, lc[LC_CB]);
         dHdT = C + dth * (P.L + T * dC);   // heat_methods.jl:105
     } else if ((kind & 0xff) == 0) {
@@ -176,7 +176,7 @@ __device__ __forceinline__ void freezethaw_body(const Dev& P, const double* lc, 
     } else if (((kind >> 8) & 0xff) == 0) {
         // SFCC + presolver: soil_heat.jl:116-140 -- T from the table, then θw, ∂θw∂T at T
         T = lut_T(P, lc, H);
-        thw = sfcc_theta(lc, T, dth);
+        thw = sfcc_theta<!EXACT>(lc, T, dth);
         C = fma(dC, thw, lc[LC_CBS]);
         dHdT = C + dth * (P.L + T * dC);   // heat_methods.jl:105
     } else {
@@ -270,7 +270,7 @@ __device__ __forceinline__ void stage_a_lut(const Dev& P, const double* lcw, con
             double n = lc[LC_N], m = lc[LC_M];
             double xs = sel_max(x[j], 1e-300);
             double xn, p;
-            vg_powers_body(xs, n, m, xn, p);
+            vg_powers_body<true>(xs, n, m, xn, p);
             bool pos = x[j] > 0.0;
             pb[j] = pos ? p : 1.0;
             if (DERIV) q[j] = pos ? m * n * lc[LC_ALPHA] * (xn * rcp_fast(xs)) * (p * rcp_fast(1.0 + xn)) : 0.0;

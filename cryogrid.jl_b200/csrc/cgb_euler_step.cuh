@@ -62,6 +62,7 @@ __global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, const
     constexpr bool ILV = (MODE == 0 || MODE == 2);
     auto cell_of = [&](int ln, int j) { return ILV ? j * 32 + ln : ln * CPL + j; };
 
+    if (MODE != 3 && MODE != 4) vgtab_init();             // exp / log tables of the van Genuchten powers (shared memory)
     for (int s = threadIdx.x; s < CPL * 32; s += blockDim.x) {
         int j = s >> 5, ln = s & 31;
         int i = cell_of(ln, j);

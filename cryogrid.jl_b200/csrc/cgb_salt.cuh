@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(128) k_salt_euler(const __grid_constant__ Dev 
     const int lane = threadIdx.x & 31;
     const int N = P.N;
     const long long M = P.M;
+    if (!DIAG) vgtab_init();                              // exp / log tables of the van Genuchten powers (stepping only)
     for (int s = threadIdx.x; s < CPL * 32; s += blockDim.x) {
         int j = s >> 5, ln = s & 31;
         int i = ln * CPL + j;
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(128) k_salt_euler(const __grid_constant__ Dev 
                 } else { psi = psi0[j]; dpsi_dT = 0.0; dpsi_dc = 0.0; }
                 double dth;
                 double thsat = sel_max(Ssat * por[j], por[j]);
-                thw[j] = vg_theta(psi, thsat, Sthres, Salpha, Sn, m, dth);
+                thw[j] = vg_theta<!DIAG>(psi, thsat, Sthres, Salpha, Sn, m, dth);
                 dthT[j] = dth * dpsi_dT;
                 dthc[j] = dth * dpsi_dc;
                 Cc[j] = fma(dC, thw[j], Cb[j]);

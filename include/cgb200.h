@@ -254,6 +254,8 @@ int cgb_selftest_rcp(const double* x, int64_t n, double* out_raw, double* out_ne
 /* Self-test: the kernels' exp / log replacements (van Genuchten powers, FreezeCurves.jl closed forms):
  * out_exp[i] = exp_fast(x[i]) (argument clamped to [-708, 709]), out_log[i] = log_pos(|x[i]|) (normal range). */
 int cgb_selftest_explog(const double* x, int64_t n, double* out_exp, double* out_log);
+/* Same for the table-driven variants the STEPPING kernels use (64-entry shared-memory tables, exp_tab / log_tab). */
+int cgb_selftest_explog_tab(const double* x, int64_t n, double* out_exp, double* out_log);
 
 /* Self-test of the SFCC single-class fast path (many columns of ONE soil class through the presolver LUT, MaxDelta limiter:
  * csrc/cgb_euler_sfcc_fast.cuh): thw_out[i] = θw(T[i]) evaluated from the shared-memory curve table exactly as the stepping

@@ -137,6 +137,25 @@ def test_exp_log_replacements_accuracy():
     assert np.all(np.isfinite(ex)) and np.all(ex > 0.0)
 
 
+def test_exp_log_table_variants_accuracy():
+    # the STEPPING kernels evaluate the van Genuchten powers with table-driven exp / log (exp_tab / log_tab: 64-entry shared-memory
+    # tables).  exp: relative error; log: ABSOLUTE error in units of max(1, |log x|) -- its results only ever feed exp(n log x) and
+    # exp(-m log(1 + x^n)), where the absolute error of the logarithm is what matters.
+    from cryogrid_jl_b200 import _lib as L
+    rng = np.random.default_rng(2)
+    x = np.concatenate([rng.uniform(-700.0, 700.0, 40000), rng.uniform(-2.0, 2.0, 20000), 10.0 ** rng.uniform(-300, 300, 20000),
+                        1.0 + rng.uniform(-1e-3, 1e-3, 20000), 1.0 + 10.0 ** rng.uniform(-16, 0, 20000), 2.0 ** rng.integers(-1000, 1000, 2000)])
+    ex, lg = np.empty_like(x), np.empty_like(x)
+    assert L.load().cgb_selftest_explog_tab(L.dptr(x), x.size, L.dptr(ex), L.dptr(lg)) == 0
+    a = np.clip(x, -708.0, 709.0)
+    e_exp = np.max(np.abs(ex - np.exp(a)) / np.exp(a))
+    ref = np.log(np.abs(x))
+    e_log = np.max(np.abs(lg - ref) / np.maximum(np.abs(ref), 1.0))
+    print(f"exp_tab rel. error {e_exp:.3e}, log_tab abs. error (units of max(1, |log|)) {e_log:.3e}")
+    assert e_exp < 7e-16 and e_log < 5e-16
+    assert np.all(np.isfinite(ex)) and np.all(ex > 0.0)
+
+
 @pytest.mark.parametrize("solver", ["lut", "newton"])
 def test_advance_sfcc_cfl_limiter(orc, solver):
     # CFL limiter on SFCC columns: the stepping kernel evaluates dH/dT only in this configuration (LUT mode)
