@@ -8,10 +8,10 @@ statement of "the engine does what the reference does on this configuration" -- 
   1. the CUDA engine integrates the configuration for one simulated year;
   2. at >= 6 checkpoints spread over the year the oracle is re-seeded from the engine's own checkpoint (u, t, dt) and both
      advance over the same window of 6 simulated hours (the oracle's own 1-ulp envelope over such a window is <= 4e-12 K and
-     <= 8e-11 relative in dt, measured in scratch/chaos.py -- i.e. the window is short enough for a strict gate);
+     <= 8e-11 relative in dt, measured in scripts/chaos_envelope_cfg2.py -- i.e. the window is short enough for a strict gate);
   3. gates: |dT| <= 1e-9 K, |dθw| <= 1e-11, EQUAL step counts, and the whole dt SEQUENCE of the window agrees to <= 2e-8
      relative -- the reference's OWN envelope under a +-3 ulp perturbation of the checkpoint reaches 2.2e-9 in the dt sequence and
-     4.6e-11 K over 6 h in the chaotic phases of the SFCC configurations (scratch/chaos_sfcc.py, oracle only), so a tighter gate
+     4.6e-11 K over 6 h in the chaotic phases of the SFCC configurations (scripts/chaos_envelope_sfcc.py, oracle only), so a tighter gate
      would test the chaos, not the engine -- (first dt of the window: bit-equal, it comes from the checkpoint; second: <= 1e-12
      relative, measured 259 ulp
      = 6e-14 -- dH = (j_i - j_{i+1})/Δk cancels the two edge fluxes, which amplifies the per-operation rounding differences
