@@ -152,16 +152,14 @@ __global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__
                     if (j == jb) as = 0.0;
                     double ap = an + as, bp = 0.0;
                     if (j == 0 && lane == 0) {                                       // heat_implicit.jl:59-64,72-79
-                        double dk = sDk[s];
                         double jtop = (P.top_kind == 0) ? 2.0 * vtop * kc[0] * idk : vtop;
                         bp += jtop * idk;
-                        if (P.top_kind == 0) ap += kc[0] / (dk * dk / 2.0);
+                        if (P.top_kind == 0) ap += kc[0] * (2.0 * idk * idk);          // k / (dk^2 / 2) without the division
                     }
                     if (j == jb) {                                                   // heat_implicit.jl:65-70,80-86 (quirks verbatim)
-                        double dk = sDk[s];
                         double jbot = (P.bot_kind == 0) ? 2.0 * vbot * kc[j] * idk : vbot;
                         bp += jbot * idk;
-                        if (P.bot_kind == 0) ap += kfirst / (dk * dk / 2.0);
+                        if (P.bot_kind == 0) ap += kfirst * (2.0 * idk * idk);
                     }
                     double sp = dHdT[j] * idt;                                       // -Sp
                     bool real = (lane * CPL + j) < N;
@@ -170,15 +168,33 @@ __global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__
                     rb[j] = real ? ap + sp : 1.0;                                    // B (reciprocal taken below)
                     d[j] = real ? fma(sp, T[j], (H0[j] - H[j]) * idt) + bp : 0.0;
                 }
-                // ---- 1. forward elimination: row j -> f_j x_p + b_j x_j + c_j x_{j+1} = d_j
-                rb[0] = rcp_fast(rb[0]);
+                // ---- 1. forward elimination: row j -> f_j x_p + den_j x_j + c_j x_{j+1} = d_j, DIVISION-FREE in the dependent chain.
+                // The textbook sweep (w = a_j / den_{j-1}; den_j = b_j - w c_{j-1}; ...) carries one reciprocal (MUFU + 4 dependent
+                // FMAs) per row: ~65 cycles x CPL with ILP 1 -- half of the latency of one Picard iteration.  With the continuant
+                // q_j = b_j q_{j-1} - a_j c_{j-1} q_{j-2} (q_{-1} = 1, q_0 = b_0) one has den_j = q_j / q_{j-1}, and the scaled
+                // unknowns F_j = f_j q_{j-1}, E_j = d_j' q_{j-1} obey F_j = -a_j F_{j-1}, E_j = d_j q_{j-1} - a_j E_{j-1}: one FMA
+                // per row in each chain, then CPL independent reciprocals.  Same algebra, rounding differs in the last bits; the
+                // systems are diagonally dominant (q_j / q_{j-1} >= b_j - |a_j|), q_j <= (max den)^CPL stays far below 1e308.
+                // In place: rb[j] <- q_j, d[j] <- E_j, fa[j] <- F_j.
 #pragma unroll
                 for (int j = 1; j < CPL; ++j) {
-                    double w = fa[j] * rb[j - 1];
-                    fa[j] = -w * fa[j - 1];
-                    d[j] = fma(-w, d[j - 1], d[j]);
-                    rb[j] = rcp_fast(fma(-w, gc[j - 1], rb[j]));
+                    const double ac = fa[j] * gc[j - 1];
+                    const double qj = (j >= 2) ? fma(rb[j], rb[j - 1], -ac * rb[j - 2]) : fma(rb[j], rb[j - 1], -ac);
+                    d[j] = fma(-fa[j], d[j - 1], d[j] * rb[j - 1]);
+                    fa[j] = -fa[j] * fa[j - 1];
+                    rb[j] = qj;
                 }
+                double rq[CPL];
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) rq[j] = rcp_fast(rb[j]);
+                const double den_last = (CPL >= 2) ? rb[CPL - 1] * rq[CPL >= 2 ? CPL - 2 : 0] : rb[0];    // q_last / q_{last-1}
+#pragma unroll
+                for (int j = CPL - 1; j >= 1; --j) {
+                    fa[j] *= rq[j - 1];
+                    d[j] *= rq[j - 1];
+                    rb[j] = rb[j - 1] * rq[j];                                       // 1 / den_j = q_{j-1} / q_j
+                }
+                rb[0] = rq[0];
                 // ---- 2. backward elimination: row j -> f_j x_p + b_j x_j + g_j x_{m-1} = d_j   (j <= m-2)
                 const double c_last = gc[CPL - 1];
 #pragma unroll
@@ -196,11 +212,11 @@ __global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__
                 double A, B, C, D;
                 if (CPL >= 2) {
                     A = fa[CPL - 1];
-                    B = fma(-c_last, nf0, 1.0 / rb[CPL - 1]);
+                    B = fma(-c_last, nf0, den_last);
                     C = -c_last * ng0;
                     D = fma(-c_last, nd0, d[CPL - 1]);
                 } else {   // one row per lane: the reduced system is the system itself
-                    A = fa[0]; B = 1.0 / rb[0]; C = c_last; D = d[0];
+                    A = fa[0]; B = den_last; C = c_last; D = d[0];
                 }
                 if (lane == 31) C = 0.0;
                 if (lane == 0) A = 0.0;
