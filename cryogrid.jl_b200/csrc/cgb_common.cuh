@@ -345,19 +345,27 @@ __device__ __forceinline__ void vgtab_init()
     __syncthreads();
 }
 
+// constants of exp_tab / log_tab in constant memory (c[bank][offset] operands): as FP64 literals every use costs two moves
+static __constant__ double CGB_TAB_C[18] = {
+    1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0,                       // 0..4   e^r - 1 series
+    -1.0 / 6.0, 0.2, -0.25, 1.0 / 3.0, -0.5,                            // 5..9   log1p series
+    92.332482616893656877,                                              // 10     64 / ln 2
+    -6.93147180369123816490e-01 / 64.0, -1.90821492927058770002e-10 / 64.0,   // 11, 12  -ln2_hi / 64 (33 significant bits), -ln2_lo / 64
+    6.93147180369123816490e-01, 1.90821492927058770002e-10,             // 13, 14 ln2_hi, ln2_lo
+    6755399441055744.0, -708.0, 709.0};                                 // 15 (1.5 * 2^52), 16, 17
+
 __device__ __forceinline__ double exp_tab(double a)
 {
-    a = sel_min(sel_max(a, -708.0), 709.0);
-    const double MAGIC = 6755399441055744.0;             // 1.5 * 2^52: round-to-nearest-integer by addition
-    const double t = fma(a, 92.332482616893656877, MAGIC);   // 64 / ln 2
+    a = sel_min(sel_max(a, CGB_TAB_C[16]), CGB_TAB_C[17]);
+    const double t = fma(a, CGB_TAB_C[10], CGB_TAB_C[15]);              // round-to-nearest-integer by adding 1.5 * 2^52
     const int k = __double2loint(t);
-    const double kd = t - MAGIC;
-    double r = fma(kd, -6.93147180369123816490e-01 / 64.0, a);       // ln2_hi / 64 (33 significant bits: kd * hi is exact)
-    r = fma(kd, -1.90821492927058770002e-10 / 64.0, r);
-    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-    p = fma(p, r, 1.0 / 6.0);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
+    const double kd = t - CGB_TAB_C[15];
+    double r = fma(kd, CGB_TAB_C[11], a);                               // kd * (ln2_hi / 64) is exact
+    r = fma(kd, CGB_TAB_C[12], r);
+    double p = fma(r, CGB_TAB_C[0], CGB_TAB_C[1]);
+    p = fma(p, r, CGB_TAB_C[2]);
+    p = fma(p, r, CGB_TAB_C[3]);
+    p = fma(p, r, CGB_TAB_C[4]);
     p = p * r;                                            // e^r - 1, |r| <= ln2 / 128 (truncation r^6/720 = 3.5e-17)
     const double T = g_vgtab[128 + (k & 63)];
     const double res = fma(T, p, T);
@@ -371,15 +379,15 @@ __device__ __forceinline__ double log_tab(double x)      // normal x > 0
     const int idx = (hi >> 14) & 63;
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
     const double2 t = *reinterpret_cast<const double2*>(&g_vgtab[2 * idx]);     // 1/c, log c
-    const double r = fma(m, t.x, -1.0);                   // |r| <= 2^-7
-    double p = fma(r, -1.0 / 6.0, 0.2);
-    p = fma(p, r, -0.25);
-    p = fma(p, r, 1.0 / 3.0);
-    p = fma(p, r, -0.5);
+    const double r = fma(m, t.x, -CGB_TAB_C[4]);          // |r| <= 2^-7
+    double p = fma(r, CGB_TAB_C[5], CGB_TAB_C[6]);
+    p = fma(p, r, CGB_TAB_C[7]);
+    p = fma(p, r, CGB_TAB_C[8]);
+    p = fma(p, r, CGB_TAB_C[9]);
     p = p * r;
     const double l1 = fma(p, r, r);                       // log1p(r), truncation r^7/7 = 2.5e-16
     const double ed = (double)e;
-    return fma(ed, 6.93147180369123816490e-01, fma(ed, 1.90821492927058770002e-10, t.y + l1));
+    return fma(ed, CGB_TAB_C[13], fma(ed, CGB_TAB_C[14], t.y + l1));
 }
 
 // x^n and (1+x^n)^-m for x > 0 through exp / log (~150 instructions with the series versions, ~75 with the tables).  Inlined
