@@ -90,6 +90,7 @@ extern "C" void cgb_destroy(cgb_handle* h)
     for (int i = 0; i < 2; ++i) {
         if (h->d_stage[i]) cudaFree(h->d_stage[i]);
         if (i == 0 && h->d_lite) cudaFree(h->d_lite);
+        if (i == 0 && h->d_selfull) cudaFree(h->d_selfull);
         if (h->stage_ready[i]) cudaEventDestroy(h->stage_ready[i]);
         if (h->stage_free[i]) cudaEventDestroy(h->stage_free[i]);
     }
@@ -1014,6 +1015,64 @@ extern "C" int cgb_solve_saveat_select(cgb_handle* h, const double* tsave, int64
     double* nowW = h->d_scratch + 3 * (size_t)(h->N + 1) * M;
     SaveVars need = sv;
     need.T |= thawdepth_out != nullptr;           // thaw depth is computed from the saved T, as Diagnostics.thawdepth(out.T) does
+    // Device-side saveat for the selected output too: up to 8 save times per stepping launch (a column stays in registers across
+    // them), the full fields of the chunk stay on the device, only the selected rows and thaw depths of the chunk are copied out
+    // (two copies per chunk).  Same conditions as in cgb_solve_saveat.
+    bool chunked = multi_target_path(h) && !sv.Tnow && !sv.Wnow && nsave >= 2 && tsave[0] > h->t_front;
+    for (auto& n : names) chunked = chunked && n != "H";
+    for (int64_t s = 1; chunked && s < nsave; ++s) chunked = tsave[s] > tsave[s - 1];
+    if (chunked) {
+        const size_t vars_save = names.size() * SM;
+        const int nfull = (need.T ? 1 : 0) + (need.W ? 1 : 0);
+        int chunk = (int)std::min<int64_t>(std::min<int64_t>(8, cgb_fast_max_targets()), nsave);
+        while (chunk > 1 && (size_t)chunk * NM * nfull * sizeof(double) > ((size_t)4 << 30)) chunk /= 2;
+        rc = ensure_staging(h, (size_t)chunk * per_save);
+        if (rc) { cudaFree(d_rows); return rc; }
+        const size_t full_elems = (size_t)chunk * NM * std::max(nfull, 1);
+        if (h->selfull_elems < full_elems) {
+            if (h->d_selfull) cudaFree(h->d_selfull);
+            h->d_selfull = nullptr; h->selfull_elems = 0;
+            if (cudaMalloc((void**)&h->d_selfull, full_elems * sizeof(double)) != cudaSuccess) { cudaGetLastError(); cudaFree(d_rows); CGB_FAIL(h, CGB_ERR_ALLOC, "full-field chunk buffer (%zu bytes)", full_elems * sizeof(double)); }
+            h->selfull_elems = full_elems;
+        }
+        double* fT = need.T ? h->d_selfull : nullptr;
+        double* fW = need.W ? h->d_selfull + (need.T ? (size_t)chunk * NM : 0) : nullptr;
+        dim3 grid((unsigned)((M + 255) / 256), (unsigned)std::max(nsel, 1));
+        int64_t c = 0;
+        for (int64_t s0 = 0; s0 < nsave; ++c) {
+            const int n = (int)std::min<int64_t>(chunk, std::max<int64_t>(1, (nsave - s0 + 1) / 2)), b = (int)(c & 1);
+            // columns that stop early leave their remaining save slots unwritten: NaN (all-ones bytes), not stale data
+            cudaMemsetAsync(h->d_selfull, 0xFF, (size_t)chunk * NM * std::max(nfull, 1) * sizeof(double), h->stream);
+            rc = launch_multi(h, tsave + s0, n, fT, fW, (long long)NM);
+            if (rc) { cudaFree(d_rows); return rc; }
+            h->t_front = tsave[s0 + n - 1];
+            if (c >= 2) cudaStreamWaitEvent(h->stream, h->stage_free[b], 0);
+            for (int k = 0; k < n; ++k) {
+                for (size_t v = 0; v < names.size(); ++v) {
+                    const double* src = (names[v] == "T" ? fT : fW) + (size_t)k * NM;
+                    k_gather_rows<<<grid, 256, 0, h->stream>>>(src, d_rows, nsel, (long long)M, h->d_stage[b] + (size_t)k * vars_save + v * SM);
+                    h->launches++;
+                }
+                if (thawdepth_out) {
+                    k_thawdepth<<<(unsigned)((M + 127) / 128), 128, 0, h->stream>>>(fT + (size_t)k * NM, h->dev.zc, h->N, (long long)M,
+                                                                                   h->d_stage[b] + (size_t)chunk * vars_save + (size_t)k * M);
+                    h->launches++;
+                }
+            }
+            cudaEventRecord(h->stage_ready[b], h->stream);
+            cudaStreamWaitEvent(h->copy_stream, h->stage_ready[b], 0);
+            if (!names.empty())
+                cudaMemcpyAsync(out + (size_t)s0 * vars_save, h->d_stage[b], (size_t)n * vars_save * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream);
+            if (thawdepth_out)
+                cudaMemcpyAsync(thawdepth_out + (size_t)s0 * M, h->d_stage[b] + (size_t)chunk * vars_save, (size_t)n * M * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream);
+            cudaEventRecord(h->stage_free[b], h->copy_stream);
+            s0 += n;
+        }
+        cudaError_t e1 = cudaStreamSynchronize(h->stream), e2 = cudaStreamSynchronize(h->copy_stream);
+        cudaFree(d_rows);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) CGB_FAIL(h, CGB_ERR_CUDA, "cgb_solve_saveat_select: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        return CGB_OK;
+    }
     for (int64_t s = 0; s < nsave; ++s) {
         int b = (int)(s & 1);
         rc = advance_and_save(h, tsave[s], need, fullT, fullW, nowT, nowW);

@@ -55,6 +55,8 @@ struct cgb_handle {
     double* d_lite = nullptr;         // LiteImplicit scratch: 5*N*M doubles
     double* d_stage[2] = {nullptr, nullptr};
     size_t stage_elems = 0;
+    double* d_selfull = nullptr;      // full saved fields of one chunk of cgb_solve_saveat_select (stay on the device)
+    size_t selfull_elems = 0;
     cudaEvent_t stage_ready[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr};
     long long launches = 0;
     bool profiling = false;
