@@ -493,7 +493,7 @@ extern "C" int cgb_init_interp(cgb_handle* h, const double* zk, const double* vk
 {
     if (!h || !zk || !vk || nk < 1) return CGB_ERR_INVALID;
     clear_stale_error("cgb_init_interp");
-    if (h->cfg.physics != CGB_PHYSICS_HEAT) CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "cgb_init_interp: heat physics only");
+    if (h->cfg.physics == CGB_PHYSICS_HEAT_SALT) CGB_FAIL(h, CGB_ERR_UNSUPPORTED, "cgb_init_interp: heat physics only");
     if (per != CGB_PER_GLOBAL && per != CGB_PER_COLUMN) CGB_FAIL(h, CGB_ERR_INVALID, "profile values are GLOBAL (nk) or COLUMN (nk*M)");
     for (int64_t k = 1; k < nk; ++k)
         if (!(zk[k] > zk[k - 1])) CGB_FAIL(h, CGB_ERR_INVALID, "profile depths must be strictly increasing");

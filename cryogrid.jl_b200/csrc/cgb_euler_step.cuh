@@ -59,7 +59,11 @@ __global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, const
     // need a second evaluation are the dynamic ones near the surface / the freezing front, i.e. neighbours; contiguous, they sit
     // in a few lanes and every slot of the warp waits for them (measured: 2.2 evaluations per cell and warp for 1.24 per
     // thread); interleaved, they fill whole slots, and a slot's iteration loop runs with all lanes busy or not at all.
-    constexpr bool ILV = (MODE == 0 || MODE == 2);
+    // (CGB_LUT_ILV: A/B knob -- the LUT modes interleaved too, so that a warp-wide knot lookup addresses adjacent cells)
+#ifndef CGB_LUT_ILV
+#define CGB_LUT_ILV 0
+#endif
+    constexpr bool ILV = (MODE == 0 || MODE == 2) || (CGB_LUT_ILV && (MODE == 1 || MODE == 4));
     auto cell_of = [&](int ln, int j) { return ILV ? j * 32 + ln : ln * CPL + j; };
 
     if (MODE != 3 && MODE != 4) vgtab_init();             // exp / log tables of the van Genuchten powers (shared memory)

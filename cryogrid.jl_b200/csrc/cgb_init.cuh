@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(256) k_init_interp(const __grid_constant__ Dev
         double w = (z - zk[lo]) / (zk[lo + 1] - zk[lo]);
         T = (1.0 - w) * V(lo) + w * V(lo + 1);
     }
+    if (P.tform) { P.u[(size_t)cell * M + col] = T; return; }      // HeatBalance(:T): the prognostic state is T itself
     double lc[LC_STRIDE];
     layer_consts(P, col, P.cell_layer[cell], lc);
     P.u[(size_t)cell * M + col] = enthalpy_from_T(P, lc, T);

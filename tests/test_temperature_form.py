@@ -110,6 +110,9 @@ def test_temperature_form_gpu_parity(orc, layers):
     eng3.set_state(T0, 0.0)
     eng3.advance_to(DAY); eng3.advance_to(5 * DAY)
     np.testing.assert_allclose(out[1, 0], eng3.get_state(), rtol=0, atol=1e-12)
+    # on-device initial condition (cgb_init_interp): for the temperature form the interpolated profile IS the state
+    eng3.initialcondition(0.0)
+    np.testing.assert_allclose(eng3.get_state(), cg.initialcondition(tile), rtol=0, atol=1e-13)
     for e in (eng, eng2, eng3):
         e.close()
 
