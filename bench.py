@@ -425,7 +425,19 @@ def main():
             a = te.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
             b = te.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
             el, cs2 = float(a[0]), float(b[1])
+        # context for the number above: what one pinned device-to-host copy of a saved field block achieves on this box
+        probe_d = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
+        probe_h = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, pin_memory=True)
+        probe_h.copy_(probe_d, non_blocking=True); torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(4):
+            probe_h.copy_(probe_d, non_blocking=True)
+        ev1.record(); torch.cuda.synchronize()
+        d2h_gbs = 4 * probe_h.numel() * 8 / (ev0.elapsed_time(ev1) / 1e3) / 1e9
+        del probe_d, probe_h
         e2e = {"value": cs2 / el, "unit": "cell-steps/s", "h2d_bytes_per_step": int(pinned_u0.nbytes),
+               "pinned_d2h_gbs_probe": d2h_gbs, "d2h_gbs_achieved": (nsave + 1) * N * M * 8 * e2e_steps * world / el / 1e9 / world,
                "d2h_bytes_per_step": int((nsave + 1) * N * M * 8), "steps": e2e_steps, "ms_per_step": 1e3 * el / e2e_steps,
                "numa": numa_note,
                "note": "solve(CryoGridProblem(saveat=1 day, savevars=T)) on the first timed window, u0 uploaded from pinned host "
