@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, os.environ.get("CGB_LIB_NAME", "libcgb200.so"))      # developer knobs for A/B builds
-SOURCES = ["cgb_api.cu", "cgb_tu_fast.cu", "cgb_tu_sfcc_fast.cu", "cgb_tu_euler.cu", "cgb_tu_euler_diag.cu", "cgb_tu_lite.cu", "cgb_tu_lite_warp.cu",
+SOURCES = ["cgb_api.cu", "cgb_tu_fast.cu", "cgb_tu_sfcc_fast.cu", "cgb_tu_newton_tab.cu", "cgb_tu_euler.cu", "cgb_tu_euler_diag.cu", "cgb_tu_lite.cu", "cgb_tu_lite_warp.cu",
            "cgb_tu_salt.cu", "cgb_tu_presolver.cu"]
 EXTRA_FLAGS = {"cgb_tu_presolver.cu": ["-fmad=false"]}      # knots must agree with the (uncontracted) host builders to rounding
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]

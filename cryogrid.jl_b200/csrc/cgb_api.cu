@@ -688,6 +688,7 @@ static int launch_multi(cgb_handle* h, const double* targets, int n, double* sav
     if (h->cfg.stepper == CGB_STEPPER_LITE_IMPLICIT) return cgb_launch_lite_warp_multi(h, targets, n, saveT, saveW, save_stride);
     if (fast_path(h)) return cgb_launch_fast_multi(h, targets, n, saveT, saveW, save_stride);
     if (h->sfcc_fast_ok) return cgb_launch_sfcc_fast_multi(h, targets, n, saveT, saveW, save_stride);
+    if (cgb_newton_tab_ok(h)) return cgb_launch_newton_tab_multi(h, targets, n, saveT, saveW, save_stride);
     Diag D{};
     D.T = saveT; D.thw = saveW;
     return cgb_launch_euler_step_multi(h, euler_mode(h), targets, n, D, save_stride);

@@ -141,3 +141,74 @@ def test_fast_path_large_ragged_batch_saved_outputs_follow_reference_cache(orc):
             assert np.max(np.abs(out[k, 0, :, c] - oc.work.get("T"))) <= 1e-9
             assert np.max(np.abs(out[k, 1, :, c] - oc.work.get("thw"))) <= 1e-11
     eng.close()
+
+
+# ---- per-column parameters: the Newton kernel with the column's own curve table (csrc/cgb_euler_newton_tab.cuh) -------------
+class general_newton:
+    def __enter__(self):
+        self.old = os.environ.get("CGB_NEWTON_TAB")
+        os.environ["CGB_NEWTON_TAB"] = "0"
+
+    def __exit__(self, *a):
+        if self.old is None:
+            os.environ.pop("CGB_NEWTON_TAB", None)
+        else:
+            os.environ["CGB_NEWTON_TAB"] = self.old
+
+
+@pytest.mark.parametrize("kind", ["dallamico", "painterkarra"])
+def test_newton_tab_matches_oracle_strict(orc, kind):
+    # cfg4 shape (per-column alpha, n, porosity, organic fraction; one layer), stable dtmax: north_star gate at every save point
+    tile = common.sfcc_tile(ncolumns=20, kind=kind, solver="newton", per_column=True, grid=cg.DefaultGrid_5cm, seed=21,
+                            top=cg.PeriodicBC(cg.Dirichlet, common.YEAR, 18.0, 0.0, -10.0), bottom=cg.GeothermalHeatFlux(0.053),
+                            temp=cg.SamoylovDefault_tempprofile)
+    tile.top_offset = np.random.default_rng(3).normal(0.0, 2.0, 20)
+    tile.sat[:, 10:] = np.random.default_rng(4).uniform(0.6, 1.0, 10)         # unsaturated columns: psi0 < 0, T* < Tm
+    H0 = cg.initialcondition(tile)
+    eng = cg.Engine(tile, dtmax=600.0)
+    w = _check_advance(orc, tile, eng, H0, 0.0, [3600.0, DAY, 5 * DAY, 20 * DAY], dtmax=600.0, cols=(0, 7, 12, 19))
+    print(f"Newton with per-column curve tables vs oracle ({kind}), 20 days:", w)
+    eng.close()
+
+
+def test_newton_tab_matches_general_newton_kernel_and_saves():
+    tile = common.cfg4_tile(96, "newton")
+    H0 = cg.initialcondition(tile)
+    res = {}
+    for name in ("tab", "general"):
+        ctx = general_newton() if name == "general" else None
+        if ctx:
+            ctx.__enter__()
+        try:
+            eng = cg.Engine(tile, dtmax=600.0)
+            eng.set_state(H0, 0.0)
+            out = eng.solve_saveat(DAY * np.arange(1, 4), ("T", "θw"))
+            H, t, dt = eng.get_state(with_time=True)
+            st, steps = eng.status()
+            assert not st.any()
+            res[name] = (out, dt, steps)
+            eng.close()
+        finally:
+            if ctx:
+                ctx.__exit__()
+    assert np.array_equal(res["tab"][2], res["general"][2])
+    assert np.max(np.abs(res["tab"][0][:, 0] - res["general"][0][:, 0])) <= 1e-9
+    assert np.max(np.abs(res["tab"][0][:, 1] - res["general"][0][:, 1])) <= 1e-11
+    np.testing.assert_allclose(res["tab"][1], res["general"][1], rtol=1e-9)
+
+
+def test_newton_tab_small_grids_and_extreme_states(orc):
+    for name, grid, dtmax in (("6 cells", cg.Grid(np.linspace(0.0, 3.0, 7)), 3600.0), ("1m", cg.DefaultGrid_1m, 3600.0), ("2cm", cg.DefaultGrid_2cm, 100.0)):
+        tile = common.sfcc_tile(ncolumns=5, kind="dallamico", solver="newton", per_column=True, grid=grid, seed=2,
+                                top=cg.PeriodicBC(cg.Dirichlet, common.YEAR, 18.0, 0.0, -10.0), bottom=cg.GeothermalHeatFlux(0.053),
+                                temp=cg.SamoylovDefault_tempprofile)
+        H0 = cg.initialcondition(tile)
+        H0[:, 1] += 3.0e8 * (np.arange(H0.shape[0]) % 3 == 0)          # thawed cells
+        H0[:, 2] -= 2.5e8 * (np.arange(H0.shape[0]) % 4 == 1)          # cells below -64 degC: outside the curve table (closed form)
+        eng = cg.Engine(tile, dtmax=dtmax)
+        try:
+            w = _check_advance(orc, tile, eng, H0, 0.0, [3600.0, DAY], dtmax=dtmax)
+        except AssertionError as e:
+            raise AssertionError(f"grid {name}: {e}") from e
+        print(f"Newton-tab, grid {name}:", w)
+        eng.close()
