@@ -419,6 +419,8 @@ static int finalize(cgb_handle* h)
     if (rc) return rc;
     rc = cgb_sfcc_fast_prepare(h);           // SFCC single-class fast path: eligibility + shared-memory tables
     if (rc) return rc;
+    rc = cgb_newton_tab_prepare(h);          // per-column curve tables of the Newton kernel: HBM cache
+    if (rc) return rc;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->dirty = false;
     return CGB_OK;

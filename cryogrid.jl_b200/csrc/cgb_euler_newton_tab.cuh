@@ -6,7 +6,7 @@
 // table -- but one WARP owns one COLUMN for a whole launch (hundreds of steps), so the warp fits the column's own curve table at
 // column start: θw(u), u = T* - (T + 273.15), on log-spaced bins (exponent + top 4 mantissa bits, 16 per octave, 2^-16 K <= u < 64 K)
 // as degree-7 polynomials in the mantissa remainder, by interpolation at 8 Chebyshev nodes of the closed form (Newton divided
-// differences with precomputed node distances, expanded to monomials; 352 bins per column, 11 per lane: ~1-2 % of a one-day launch).
+// differences with precomputed node distances, expanded to monomials; 352 bins per column, 11 per lane; fitted once and kept in HBM).
 // A Newton evaluation is then a table row (4 x 16-byte shared-memory loads) + two Horner chains (θw and dθw/du): ~45 instructions.
 // Same table form as the single-class fast path (cgb_euler_sfcc_fast.cuh), same interleaved cell -> lane mapping (32 adjacent
 // cells per warp-wide load address neighbouring rows).  Outside the table (within 15 µK of T*, or below -64 °C) the closed form is
@@ -89,7 +89,8 @@ __device__ __forceinline__ void nt_fit_bin(const ColumnCurve& f, int E, int k, d
 
 template <int CPL, int WARPS, bool SAVE>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_heat_newton_tab(const __grid_constant__ Dev P, const __grid_constant__ FastTargets TG,
-                                                                  double* __restrict__ saveT, double* __restrict__ saveW)
+                                                                  double* __restrict__ saveT, double* __restrict__ saveW,
+                                                                  double* __restrict__ cache, int cache_valid)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     vgtab_init();
@@ -135,7 +136,20 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_heat_newton_tab(const __grid_
         f.thres = lc[LC_THRES]; f.d = sel_max(lc[LC_THWI], lc[LC_POR]) - lc[LC_THRES]; f.alpha = lc[LC_ALPHA]; f.n = lc[LC_N]; f.m = lc[LC_M];
         f.apsi0 = fabs(lc[LC_PSI0]); f.cfac = lc[LC_CFAC];
         __syncwarp();
-        for (int b = lane; b < NT_ROWS; b += 32) nt_fit_bin(f, NT_EMIN + (b >> 4), b & 15, tab + b * NT_STRIDE);
+        // The table is fitted in the first launch after the description changed and kept in HBM (22.5 KB per column, when it
+        // fits: cgb_newton_tab_prepare); later launches (one per save interval) read it back with 16-byte loads.
+        double2* __restrict__ crow = cache ? reinterpret_cast<double2*>(cache + (size_t)col * (NT_ROWS * 8)) : nullptr;
+        if (crow && cache_valid) {
+            for (int q = lane; q < NT_ROWS * 4; q += 32)
+                *reinterpret_cast<double2*>(tab + (q >> 2) * NT_STRIDE + (q & 3) * 2) = __ldcs(crow + q);
+        } else {
+            for (int b = lane; b < NT_ROWS; b += 32) nt_fit_bin(f, NT_EMIN + (b >> 4), b & 15, tab + b * NT_STRIDE);
+            if (crow) {
+                __syncwarp();
+                for (int q = lane; q < NT_ROWS * 4; q += 32)
+                    __stcs(crow + q, *reinterpret_cast<const double2*>(tab + (q >> 2) * NT_STRIDE + (q & 3) * 2));
+            }
+        }
         __syncwarp();
 
         double H[CPL], T[CPL], kc[CPL], dHdT[CPL], thw[SAVE ? CPL : 1];
@@ -182,31 +196,35 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_heat_newton_tab(const __grid_
             return v;
         };
 
-        // θw(T) and dθw/dT on the frozen branch: table row + two Horner chains, closed form outside the table
+        // θw and dθw/dT from the table row of u (bin must be in range): 4 x 16-byte loads, Horner with the derivative carried
+        // by synthetic division (q <- q r + p; p <- p r + c)
+        auto table_eval = [&](int bin, int uh, int ul, double& dth) -> double {
+            const double m = __hiloint2double((uh & 0x000fffff) | 0x3ff00000, ul);
+            const double c = __hiloint2double(0x3ff08000 | (uh & 0x000f0000), 0);
+            const double r = m - c;
+            const double* cf = tab + bin * NT_STRIDE;
+            const double2 c01 = *reinterpret_cast<const double2*>(cf), c23 = *reinterpret_cast<const double2*>(cf + 2);
+            const double2 c45 = *reinterpret_cast<const double2*>(cf + 4), c67 = *reinterpret_cast<const double2*>(cf + 6);
+            double p = fma(c67.y, r, c67.x), q = c67.y;
+            q = fma(q, r, p); p = fma(p, r, c45.y);
+            q = fma(q, r, p); p = fma(p, r, c45.x);
+            q = fma(q, r, p); p = fma(p, r, c23.y);
+            q = fma(q, r, p); p = fma(p, r, c23.x);
+            q = fma(q, r, p); p = fma(p, r, c01.y);
+            q = fma(q, r, p); p = fma(p, r, c01.x);
+            // dθ/du = p'(r) / 2^E ; 2^-E from the exponent field of u ; dθ/dT = -dθ/du
+            const double inv_scale = __hiloint2double((2046 - ((uh >> 20) & 0x7ff)) << 20, 0);
+            dth = -(q * inv_scale);
+            return p;
+        };
+        // the same with the closed form outside the table
         auto curve = [&](double Tq, double& dth) -> double {
             const double u = tstarK - (Tq + 273.15);
             const int uh = __double2hiint(u), ul = __double2loint(u);
             const int bin = (uh >> 16) - NT_IDX_BASE;
             double th;
-            if (bin >= 0 && bin < NT_ROWS) {
-                const double m = __hiloint2double((uh & 0x000fffff) | 0x3ff00000, ul);
-                const double c = __hiloint2double(0x3ff08000 | (uh & 0x000f0000), 0);
-                const double r = m - c;
-                const double* cf = tab + bin * NT_STRIDE;
-                const double2 c01 = *reinterpret_cast<const double2*>(cf), c23 = *reinterpret_cast<const double2*>(cf + 2);
-                const double2 c45 = *reinterpret_cast<const double2*>(cf + 4), c67 = *reinterpret_cast<const double2*>(cf + 6);
-                double p = fma(c67.y, r, c67.x), q = 7.0 * c67.y;
-                q = fma(q, r, 6.0 * c67.x);
-                p = fma(p, r, c45.y); q = fma(q, r, 5.0 * c45.y);
-                p = fma(p, r, c45.x); q = fma(q, r, 4.0 * c45.x);
-                p = fma(p, r, c23.y); q = fma(q, r, 3.0 * c23.y);
-                p = fma(p, r, c23.x); q = fma(q, r, 2.0 * c23.x);
-                p = fma(p, r, c01.y); q = fma(q, r, c01.y);
-                p = fma(p, r, c01.x);
-                th = p;
-                // dθ/du = p'(r) / 2^E ; 2^-E from the exponent field of u
-                const double inv_scale = __hiloint2double((2046 - ((uh >> 20) & 0x7ff)) << 20, 0);
-                dth = -(q * inv_scale);                                    // dθ/dT = -dθ/du
+            if ((unsigned)bin < (unsigned)NT_ROWS) {
+                th = table_eval(bin, uh, ul, dth);
             } else if (u > 0.0) {
                 double dthdu;
                 th = f.eval(u, dthdu);
@@ -217,41 +235,74 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_heat_newton_tab(const __grid_
             return th;
         };
 
-        // H -> T (safeguarded Newton seeded by the predictor), θw, kc, dH/dT for all local cells
+        // H -> T, θw, kc, dH/dT for all local cells.  Pass 1: ONE Newton step from the predictor for every slot, branch-free
+        // (seven independent dependency chains per lane: this kernel runs 8 warps per SM, so the latency has to be covered by
+        // instruction-level parallelism).  A lane is finished when the step was inside the table, inside (-273, T*) and no longer
+        // than the tolerance -- the stopping rule of the safeguarded iteration below.  Pass 2: that iteration (bracket restarted)
+        // for the slots where some lane is not finished: the top 32-64 cells in most steps, nothing below.
+        const double rcpCu = rcp_fast(Cu);
         auto stage_a = [&]() {
+            unsigned again = 0;
+            double thl[CPL];
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
                 const double Hj = H[j];
-                double Tj = T[j], th = thu, Cj = Cu, dH = Cu, dth = 0.0;
                 const bool frozen = Hj < hstar;
-                if (!frozen) Tj = (Hj - L * thu) * rcp_fast(Cu);           // thawed branch: linear in T
-                double lo = -273.0, hi = tstarC;
-                if (frozen && !(Tj > lo && Tj < hi)) Tj = hi;              // a cell that has just crossed the kink starts at it
-                bool active = frozen;
-                for (int it = 0; it < 200 && __any_sync(FULL, active); ++it) {
-                    if (active) {
-                        th = curve(Tj, dth);
-                        Cj = fma(dC, th, cbs);
-                        const double r = fma(Tj, Cj, L * th) - Hj;
-                        dH = fma(dth, fma(Tj, dC, L), Cj);                 // heat_methods.jl:105
-                        if (r > 0.0) hi = Tj; else lo = Tj;
-                        double Tn = fma(-r, rcp_fast(dH), Tj);
-                        const double tol = 1e-9 * sel_max(1.0, fabs(Tn));
-                        const bool small = fabs(Tn - Tj) <= tol;
-                        const bool safe = (Tn > lo && Tn < hi) || (small && Tn >= lo && Tn <= hi);
-                        if (!safe) Tn = 0.5 * (lo + hi);
-                        const double dT = Tn - Tj;
-                        Tj = Tn;
-                        if (fabs(dT) <= tol) {                             // converged (or the bracket has collapsed)
-                            th = fma(dth, dT, th);
-                            Cj = fma(dC, th, cbs);
-                            active = false;
+                double T0 = T[j];
+                if (!(T0 > -273.0 && T0 < tstarC)) T0 = tstarC;            // a cell that has just crossed the kink starts at it
+                const double u = tstarK - (T0 + 273.15);
+                const int uh = __double2hiint(u), ul = __double2loint(u);
+                const int bin = (uh >> 16) - NT_IDX_BASE;
+                const bool inr = (unsigned)bin < (unsigned)NT_ROWS;
+                double dth;
+                const double th = table_eval(inr ? bin : 0, uh, ul, dth);
+                const double Cj = fma(dC, th, cbs);
+                const double r = fma(T0, Cj, L * th) - Hj;
+                const double dH = fma(dth, fma(T0, dC, L), Cj);            // heat_methods.jl:105
+                const double Tn = fma(-r, rcp_fast(dH), T0);
+                const double dT = Tn - T0;
+                const bool inside = inr && Tn > -273.0 && Tn < tstarC;
+                const bool conv = inside && fabs(dT) <= 1e-9 * sel_max(1.0, fabs(Tn));
+                const double Tt = (Hj - L * thu) * rcpCu;                  // thawed branch: linear in T
+                T[j] = frozen ? (inside ? Tn : T0) : Tt;
+                thl[j] = frozen ? fma(dth, dT, th) : thu;
+                dHdT[j] = frozen ? dH : Cu;
+                if (frozen && !conv) again |= 1u << j;
+            }
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                bool active = (again >> j) & 1u;
+                if (__any_sync(FULL, active)) {
+                    const double Hj = H[j];
+                    double Tj = T[j], th = thl[j], dH = dHdT[j], dth = 0.0;
+                    double lo = -273.0, hi = tstarC;
+                    for (int it = 0; it < 200 && __any_sync(FULL, active); ++it) {
+                        if (active) {
+                            th = curve(Tj, dth);
+                            const double Cj = fma(dC, th, cbs);
+                            const double r = fma(Tj, Cj, L * th) - Hj;
+                            dH = fma(dth, fma(Tj, dC, L), Cj);
+                            if (r > 0.0) hi = Tj; else lo = Tj;
+                            double Tn = fma(-r, rcp_fast(dH), Tj);
+                            const double tol = 1e-9 * sel_max(1.0, fabs(Tn));
+                            const bool small = fabs(Tn - Tj) <= tol;
+                            const bool safe = (Tn > lo && Tn < hi) || (small && Tn >= lo && Tn <= hi);
+                            if (!safe) Tn = 0.5 * (lo + hi);
+                            const double dT = Tn - Tj;
+                            Tj = Tn;
+                            if (fabs(dT) <= tol) {                             // converged (or the bracket has collapsed)
+                                th = fma(dth, dT, th);
+                                active = false;
+                            }
                         }
                     }
+                    T[j] = Tj; dHdT[j] = dH; thl[j] = th;
                 }
-                T[j] = Tj; dHdT[j] = dH;
-                if (SAVE) thw[j] = th;
-                const double sk = fma(dK, th, kb);
+            }
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                if (SAVE) thw[j] = thl[j];
+                const double sk = fma(dK, thl[j], kb);
                 kc[j] = sk * sk;
             }
         };

@@ -45,6 +45,8 @@ struct cgb_handle {
     bool sfcc_fast_ok = false; // SFCC single-class fast kernel applicable (set by finalize -> cgb_sfcc_fast_prepare)
     cgb::SfccFast sf{};
     int sf_threads = 384;
+    double* nt_cache = nullptr;       // per-column curve tables of k_heat_newton_tab (cgb_newton_tab_prepare); freed with the description
+    bool nt_cache_valid = false;
     // device memory
     std::vector<void*> allocs;
     size_t n_state_allocs = 0;   // allocations made by cgb_create (the rest belong to the description)

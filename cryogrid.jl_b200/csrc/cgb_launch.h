@@ -19,5 +19,6 @@ int cgb_salt_diag_to(cgb_handle* h, const char* var, double t, double* dev_out);
 int cgb_sfcc_fast_prepare(cgb_handle* h);                                                          // cgb_tu_sfcc_fast.cu (called by finalize)
 int cgb_launch_sfcc_fast_multi(cgb_handle* h, const double* targets, int n, double* saveT, double* saveW, long long save_stride);
 int cgb_sfcc_fast_selftest(cgb_handle* h, const double* T, long long n, double* out);
-bool cgb_newton_tab_ok(const cgb_handle* h);                                                       // cgb_tu_newton_tab.cu
+bool cgb_newton_tab_ok(const cgb_handle* h);
+int cgb_newton_tab_prepare(cgb_handle* h);                                                       // cgb_tu_newton_tab.cu
 int cgb_launch_newton_tab_multi(cgb_handle* h, const double* targets, int n, double* saveT, double* saveW, long long save_stride);

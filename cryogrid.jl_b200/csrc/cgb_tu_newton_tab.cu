@@ -19,6 +19,21 @@ bool cgb_newton_tab_ok(const cgb_handle* h)
     return h->cfg.bot_kind == CGB_BC_NEUMANN && (h->params.count("bot_value") || h->forc[1].kind == 0);
 }
 
+// Room for every column's fitted curve table (NT_ROWS x 8 doubles) in HBM, when that is a small part of what is free: the
+// first launch after the description changed fits and stores, later launches load.  CGB_NT_CACHE=0: fit in every launch.
+int cgb_newton_tab_prepare(cgb_handle* h)
+{
+    h->nt_cache = nullptr; h->nt_cache_valid = false;
+    if (!cgb_newton_tab_ok(h)) return CGB_OK;
+    const char* e = getenv("CGB_NT_CACHE");
+    if (e && atoi(e) == 0) return CGB_OK;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return CGB_OK; }
+    const size_t need = (size_t)h->M * NT_ROWS * 8 * sizeof(double);
+    if (need > free_b / 4) return CGB_OK;
+    return dev_alloc(h, &h->nt_cache, (size_t)h->M * NT_ROWS * 8);
+}
+
 template <int CPL, bool SAVE>
 static int launch_nt_s(cgb_handle* h, const FastTargets& tg, double* saveT, double* saveW)
 {
@@ -27,9 +42,10 @@ static int launch_nt_s(cgb_handle* h, const FastTargets& tg, double* saveT, doub
     CUDA_TRY(h, cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = std::min<long long>((h->M + kNtWarps - 1) / kNtWarps, (long long)h->num_sms);
     CUDA_TRY(h, cudaMemsetAsync(h->dev.counter, 0, sizeof(unsigned long long), h->stream));
-    kern<<<(unsigned)grid, kNtWarps * 32, smem, h->stream>>>(h->dev, tg, saveT, saveW);
+    kern<<<(unsigned)grid, kNtWarps * 32, smem, h->stream>>>(h->dev, tg, saveT, saveW, h->nt_cache, h->nt_cache_valid ? 1 : 0);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
+    if (h->nt_cache) h->nt_cache_valid = true;
     return CGB_OK;
 }
 
