@@ -168,6 +168,15 @@ __device__ __forceinline__ double rcp_fast(double a)
     return y;
 }
 
+// One Newton step on MUFU.RCP64H: relative error ~1e-13 -- for Newton corrections and predictors, where the quotient is a small
+// increment of the result.
+__device__ __forceinline__ double rcp_fast1(double a)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    return fma(y, fma(-a, y, 1.0), y);
+}
+
 // Cubic (Halley-type) refinement: y1 = y0 (1 + e + e^2), e = 1 - a y0  -- 3 FMAs, error e0^3.
 __device__ __forceinline__ double rcp_fast3(double a)
 {

@@ -248,55 +248,57 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_heat_newton_tab(const __grid_
             for (int j = 0; j < CPL; ++j) {
                 const double Hj = H[j];
                 const bool frozen = Hj < hstar;
-                double T0 = T[j];
-                if (!(T0 > -273.0 && T0 < tstarC)) T0 = tstarC;            // a cell that has just crossed the kink starts at it
+                const double T0 = T[j];
                 const double u = tstarK - (T0 + 273.15);
                 const int uh = __double2hiint(u), ul = __double2loint(u);
                 const int bin = (uh >> 16) - NT_IDX_BASE;
-                const bool inr = (unsigned)bin < (unsigned)NT_ROWS;
+                const bool inr = (unsigned)bin < (unsigned)NT_ROWS;      // false for T0 >= T*, T0 < T* - 64 K and NaN
                 double dth;
                 const double th = table_eval(inr ? bin : 0, uh, ul, dth);
                 const double Cj = fma(dC, th, cbs);
                 const double r = fma(T0, Cj, L * th) - Hj;
                 const double dH = fma(dth, fma(T0, dC, L), Cj);            // heat_methods.jl:105
-                const double Tn = fma(-r, rcp_fast(dH), T0);
-                const double dT = Tn - T0;
-                const bool inside = inr && Tn > -273.0 && Tn < tstarC;
-                const bool conv = inside && fabs(dT) <= 1e-9 * sel_max(1.0, fabs(Tn));
+                const double dT = -r * rcp_fast1(dH);
+                const double Tn = T0 + dT;
+                const bool conv = inr & (Tn < tstarC) & (fabs(dT) <= 1e-9 * sel_max(1.0, fabs(Tn)));   // no short circuit: branch-free
                 const double Tt = (Hj - L * thu) * rcpCu;                  // thawed branch: linear in T
-                T[j] = frozen ? (inside ? Tn : T0) : Tt;
+                T[j] = frozen ? (inr ? Tn : T0) : Tt;
                 thl[j] = frozen ? fma(dth, dT, th) : thu;
                 dHdT[j] = frozen ? dH : Cu;
-                if (frozen && !conv) again |= 1u << j;
+                again |= (unsigned)(frozen & !conv) << j;
             }
+            again = __reduce_or_sync(FULL, again);
+            if (again) {
 #pragma unroll
-            for (int j = 0; j < CPL; ++j) {
-                bool active = (again >> j) & 1u;
-                if (__any_sync(FULL, active)) {
-                    const double Hj = H[j];
-                    double Tj = T[j], th = thl[j], dH = dHdT[j], dth = 0.0;
-                    double lo = -273.0, hi = tstarC;
-                    for (int it = 0; it < 200 && __any_sync(FULL, active); ++it) {
-                        if (active) {
-                            th = curve(Tj, dth);
-                            const double Cj = fma(dC, th, cbs);
-                            const double r = fma(Tj, Cj, L * th) - Hj;
-                            dH = fma(dth, fma(Tj, dC, L), Cj);
-                            if (r > 0.0) hi = Tj; else lo = Tj;
-                            double Tn = fma(-r, rcp_fast(dH), Tj);
-                            const double tol = 1e-9 * sel_max(1.0, fabs(Tn));
-                            const bool small = fabs(Tn - Tj) <= tol;
-                            const bool safe = (Tn > lo && Tn < hi) || (small && Tn >= lo && Tn <= hi);
-                            if (!safe) Tn = 0.5 * (lo + hi);
-                            const double dT = Tn - Tj;
-                            Tj = Tn;
-                            if (fabs(dT) <= tol) {                             // converged (or the bracket has collapsed)
-                                th = fma(dth, dT, th);
-                                active = false;
+                for (int j = 0; j < CPL; ++j) {
+                    if ((again >> j) & 1u) {
+                        const double Hj = H[j];
+                        double Tj = T[j], th = thl[j], dH = dHdT[j], dth = 0.0;
+                        double lo = -273.0, hi = tstarC;
+                        bool active = Hj < hstar;                              // lanes that are finished just confirm
+                        if (active && !(Tj > lo && Tj < hi)) Tj = hi;          // a cell that has just crossed the kink starts at it
+                        for (int it = 0; it < 200 && __any_sync(FULL, active); ++it) {
+                            if (active) {
+                                th = curve(Tj, dth);
+                                const double Cj = fma(dC, th, cbs);
+                                const double r = fma(Tj, Cj, L * th) - Hj;
+                                dH = fma(dth, fma(Tj, dC, L), Cj);
+                                if (r > 0.0) hi = Tj; else lo = Tj;
+                                double Tn = fma(-r, rcp_fast1(dH), Tj);
+                                const double tol = 1e-9 * sel_max(1.0, fabs(Tn));
+                                const bool small = fabs(Tn - Tj) <= tol;
+                                const bool safe = (Tn > lo && Tn < hi) || (small && Tn >= lo && Tn <= hi);
+                                if (!safe) Tn = 0.5 * (lo + hi);
+                                const double dT = Tn - Tj;
+                                Tj = Tn;
+                                if (fabs(dT) <= tol) {                         // converged (or the bracket has collapsed)
+                                    th = fma(dth, dT, th);
+                                    active = false;
+                                }
                             }
                         }
+                        T[j] = Tj; dHdT[j] = dH; thl[j] = th;
                     }
-                    T[j] = Tj; dHdT[j] = dH; thl[j] = th;
                 }
             }
 #pragma unroll
@@ -347,7 +349,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_heat_newton_tab(const __grid_
                 ad[j] = fabs(dH);
                 const double inc = dt * dH;
                 H[j] += inc;                                                          // basic_solvers.jl:66
-                T[j] = fma(inc, rcp_fast(dHdT[j]), T[j]);                             // first-order predictor = next Newton seed
+                T[j] = fma(inc, rcp_fast1(dHdT[j]), T[j]);                            // first-order predictor = next Newton seed
             }
 #pragma unroll
             for (int w = 1; w < CPL; w *= 2)

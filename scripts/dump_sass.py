@@ -26,6 +26,7 @@ KERNELS = {
     "k_heat_step_7_1": ("void cgb::k_heat_step<7, 1>(", 7, 1, "general SFCC presolver-LUT kernel (several soil classes); the body holds both the MaxDelta and the CFL variant of stage A"),
     "k_heat_step_7_4": ("void cgb::k_heat_step<7, 4>(", 7, 1, "general SFCC presolver-LUT kernel, every van Genuchten n == 2; the body holds both the MaxDelta and the CFL variant of stage A"),
     "k_heat_step_7_2": ("void cgb::k_heat_step<7, 2>(", 7, 1, "SFCC on-device Newton kernel, BASELINE cfg4 (per-column parameters)"),
+    "k_heat_newton_tab_7": ("void cgb::k_heat_newton_tab<7, 8, false>(", 7, 1, "SFCC Newton kernel on per-column curve tables, BASELINE cfg4 (per-column parameters); the loop holds pass 1 (branch-free) and the seven pass-2 bodies, of which ~1.6 run per step"),
     "k_lite_warp_9_3_2": ("void cgb::k_lite_warp<9, 3, 2, false>(", 9, 1, "LiteImplicitEuler warp-per-column kernel, BASELINE cfg3 (N = 278); loop = one Picard iteration"),
     "k_salt_euler_6": ("void cgb::k_salt_euler<6, false>(", 6, 1, "coupled heat + salt kernel, BASELINE cfg5 (N = 178)"),
 }
