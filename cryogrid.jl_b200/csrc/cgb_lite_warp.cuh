@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__
                     double k1 = (j == 0) ? kup : kc[j - 1];
                     int s = j * 32 + lane;
                     double w1 = sW1[s], w2 = sW2[s], g = sG[s];
-                    double r = rcp_fast(fma(w2, k1, w1 * kc[j]));
+                    double r = rcp_fast3(fma(w2, k1, w1 * kc[j]));
                     double kk = k1 * kc[j];
                     kd[j] = (kk * g) * r;                                            // 0 on non-interior edges
                     if (P.bot_kind == 0 && lane * CPL + j == ef) kfirst = (ef == 0) ? kc[j] : (kk * (w1 + w2)) * r;
@@ -148,8 +148,9 @@ __global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__
                 for (int j = 0; j < CPL; ++j) {
                     int s = j * 32 + lane;
                     double idk = sIdk[s];
+                    // padding rows (idk = 0) and the edge below the bottom cell (kd = 0: sG is 0 on non-interior edges) need no
+                    // select: an = as = 0 there, the row reduces to (dHdT/dt) x = (dHdT/dt) T
                     double an = kd[j] * idk, as = kd[j + 1] * idk;                   // heat_implicit.jl:10-24
-                    if (j == jb) as = 0.0;
                     double ap = an + as, bp = 0.0;
                     if (j == 0 && lane == 0) {                                       // heat_implicit.jl:59-64,72-79
                         double jtop = (P.top_kind == 0) ? 2.0 * vtop * kc[0] * idk : vtop;
@@ -162,11 +163,10 @@ __global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__
                         if (P.bot_kind == 0) ap += kfirst * (2.0 * idk * idk);
                     }
                     double sp = dHdT[j] * idt;                                       // -Sp
-                    bool real = (lane * CPL + j) < N;
-                    fa[j] = real ? -an : 0.0;
-                    gc[j] = real ? -as : 0.0;
-                    rb[j] = real ? ap + sp : 1.0;                                    // B (reciprocal taken below)
-                    d[j] = real ? fma(sp, T[j], (H0[j] - H[j]) * idt) + bp : 0.0;
+                    fa[j] = -an;
+                    gc[j] = -as;
+                    rb[j] = ap + sp;                                                 // B (reciprocal taken below)
+                    d[j] = fma(sp, T[j], (H0[j] - H[j]) * idt) + bp;
                 }
                 // ---- 1. forward elimination: row j -> f_j x_p + den_j x_j + c_j x_{j+1} = d_j, DIVISION-FREE in the dependent chain.
                 // The textbook sweep (w = a_j / den_{j-1}; den_j = b_j - w c_{j-1}; ...) carries one reciprocal (MUFU + 4 dependent
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__
                 }
                 double rq[CPL];
 #pragma unroll
-                for (int j = 0; j < CPL; ++j) rq[j] = rcp_fast(rb[j]);
+                for (int j = 0; j < CPL; ++j) rq[j] = rcp_fast3(rb[j]);
                 const double den_last = (CPL >= 2) ? rb[CPL - 1] * rq[CPL >= 2 ? CPL - 2 : 0] : rb[0];    // q_last / q_{last-1}
 #pragma unroll
                 for (int j = CPL - 1; j >= 1; --j) {
@@ -222,17 +222,18 @@ __global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__
                 if (lane == 0) A = 0.0;
 #pragma unroll
                 for (int s = 1; s < 32; s <<= 1) {                                   // parallel cyclic reduction
-                    double rB = rcp_fast(B);
+                    double rB = rcp_fast3(B);
                     double Au = __shfl_up_sync(FULL, A, s), Cu = __shfl_up_sync(FULL, C, s), Du = __shfl_up_sync(FULL, D, s), rBu = __shfl_up_sync(FULL, rB, s);
                     double Ad = __shfl_down_sync(FULL, A, s), Cd = __shfl_down_sync(FULL, C, s), Dd = __shfl_down_sync(FULL, D, s), rBd = __shfl_down_sync(FULL, rB, s);
                     bool hu = lane >= s, hd = lane + s < 32;
+                    // a lane without a neighbour at distance s gets its own (finite) values back from the shuffle: a zero multiplier is enough
                     double al = hu ? -A * rBu : 0.0, ga = hd ? -C * rBd : 0.0;
-                    B = B + al * (hu ? Cu : 0.0) + ga * (hd ? Ad : 0.0);
-                    D = D + al * (hu ? Du : 0.0) + ga * (hd ? Dd : 0.0);
-                    A = al * (hu ? Au : 0.0);
-                    C = ga * (hd ? Cd : 0.0);
+                    B = B + al * Cu + ga * Ad;
+                    D = D + al * Du + ga * Dd;
+                    A = al * Au;
+                    C = ga * Cd;
                 }
-                const double y = D * rcp_fast(B);
+                const double y = D * rcp_fast3(B);
                 double xp = __shfl_up_sync(FULL, y, 1);
                 if (lane == 0) xp = 0.0;
                 // ---- 4. back-substitution + Picard update (cglite_step.jl:58-72)
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__
                     double x;
                     if (CPL >= 2) x = (j == CPL - 1) ? y : (d[j] - fa[j] * xp - gc[j] * y) * rb[j];
                     else x = y;
-                    if ((lane * CPL + j) < N) {
+                    {
                         double e = x - T[j];
                         H[j] = fma(dHdT[j], e, H[j]);
                         em = sel_max(fabs(e), em);
