@@ -151,22 +151,23 @@ __global__ void __launch_bounds__(128, MINB) k_lite_warp(const __grid_constant__
                     // padding rows (idk = 0) and the edge below the bottom cell (kd = 0: sG is 0 on non-interior edges) need no
                     // select: an = as = 0 there, the row reduces to (dHdT/dt) x = (dHdT/dt) T
                     double an = kd[j] * idk, as = kd[j + 1] * idk;                   // heat_implicit.jl:10-24
-                    double ap = an + as, bp = 0.0;
+                    double sp = dHdT[j] * idt;                                       // -Sp
+                    double bj = (an + as) + sp;                                      // B = ap + dHdT/dt (reciprocal taken below)
+                    double dj = fma(sp, T[j], (H0[j] - H[j]) * idt);                 // D without bp: bp is zero except in the two boundary rows
                     if (j == 0 && lane == 0) {                                       // heat_implicit.jl:59-64,72-79
                         double jtop = (P.top_kind == 0) ? 2.0 * vtop * kc[0] * idk : vtop;
-                        bp += jtop * idk;
-                        if (P.top_kind == 0) ap += kc[0] * (2.0 * idk * idk);          // k / (dk^2 / 2) without the division
+                        dj = fma(jtop, idk, dj);
+                        if (P.top_kind == 0) bj = fma(kc[0], 2.0 * idk * idk, bj);     // k / (dk^2 / 2) without the division
                     }
                     if (j == jb) {                                                   // heat_implicit.jl:65-70,80-86 (quirks verbatim)
                         double jbot = (P.bot_kind == 0) ? 2.0 * vbot * kc[j] * idk : vbot;
-                        bp += jbot * idk;
-                        if (P.bot_kind == 0) ap += kfirst * (2.0 * idk * idk);
+                        dj = fma(jbot, idk, dj);
+                        if (P.bot_kind == 0) bj = fma(kfirst, 2.0 * idk * idk, bj);
                     }
-                    double sp = dHdT[j] * idt;                                       // -Sp
                     fa[j] = -an;
                     gc[j] = -as;
-                    rb[j] = ap + sp;                                                 // B (reciprocal taken below)
-                    d[j] = fma(sp, T[j], (H0[j] - H[j]) * idt) + bp;
+                    rb[j] = bj;
+                    d[j] = dj;
                 }
                 // ---- 1. forward elimination: row j -> f_j x_p + den_j x_j + c_j x_{j+1} = d_j, DIVISION-FREE in the dependent chain.
                 // The textbook sweep (w = a_j / den_{j-1}; den_j = b_j - w c_{j-1}; ...) carries one reciprocal (MUFU + 4 dependent
