@@ -900,7 +900,8 @@ extern "C" int cgb_solve_saveat(cgb_handle* h, const double* tsave, int64_t nsav
     for (auto& n : sv.names) chunked = chunked && n != "H";   // H is the live state: it must be copied out after every save
     for (int64_t s = 1; chunked && s < nsave; ++s) chunked = tsave[s] > tsave[s - 1];
     if (chunked && nsave >= 2 && tsave[0] > h->t_front) {
-        int chunk = (int)std::min<int64_t>(std::min<int64_t>(8, cgb_fast_max_targets()), nsave);
+        static const int chunk_max = [] { const char* e = getenv("CGB_SAVE_CHUNK"); int v = e ? atoi(e) : 8; return v >= 1 ? v : 8; }();   // developer knob
+        int chunk = (int)std::min<int64_t>(std::min<int64_t>(chunk_max, cgb_fast_max_targets()), nsave);
         // 2 x chunk x per_save doubles of staging: halve the chunk when the device cannot hold that (10^6 columns: GBs per save)
         while ((rc = ensure_staging(h, per_save * chunk)) != CGB_OK && chunk > 1) chunk = std::max(1, chunk / 2);
         if (rc) return rc;
@@ -1027,7 +1028,8 @@ extern "C" int cgb_solve_saveat_select(cgb_handle* h, const double* tsave, int64
     if (chunked) {
         const size_t vars_save = names.size() * SM;
         const int nfull = (need.T ? 1 : 0) + (need.W ? 1 : 0);
-        int chunk = (int)std::min<int64_t>(std::min<int64_t>(8, cgb_fast_max_targets()), nsave);
+        static const int chunk_max = [] { const char* e = getenv("CGB_SAVE_CHUNK"); int v = e ? atoi(e) : 8; return v >= 1 ? v : 8; }();   // developer knob
+        int chunk = (int)std::min<int64_t>(std::min<int64_t>(chunk_max, cgb_fast_max_targets()), nsave);
         while (chunk > 1 && (size_t)chunk * NM * nfull * sizeof(double) > ((size_t)4 << 30)) chunk /= 2;
         rc = ensure_staging(h, (size_t)chunk * per_save);
         if (rc) { cudaFree(d_rows); return rc; }

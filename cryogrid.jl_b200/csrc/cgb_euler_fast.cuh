@@ -158,75 +158,97 @@ __global__ void __launch_bounds__(128, MINB) k_heat_euler_fast(const __grid_cons
         const double t_target = TG.t[kt];
         // unrolled x3: the loop-carried copies of the software pipeline (next -> current T, kc, boundary value) disappear into
         // register renaming across the copies (47 of 399 instructions per step were moves); measured 3.52 -> 3.62e11 (x2: 3.59, x4: 3.61)
-#pragma unroll 3
-        while (t < t_target) {
-            if (fkind == 2 && (t < ft_first || t > ft_last)) { status |= 4; break; }     // providers.jl:30-33
-            if (SAVE && !(t + dt < t_target)) {
-                // Last step of the interval: what the reference SAVES for diagnostic variables is the cache of this (the last)
-                // RHS evaluation, i.e. T, θw of the state BEFORE the step (problem.jl:67-68 -> Numerics/statevars.jl:81-106
-                // retrieve(); CGEuler evaluates the tile before u += dt*du, basic_solvers.jl:61-66).  Reproduced verbatim.
+        // one explicit Euler step of the column at time t with step dt (fluxes, update, limiter, next dt) -- also computes T, kc and
+        // the boundary value of the NEXT step (software pipeline)
+        auto one_step = [&]() {
+                // ---- edge fluxes (upper edge of every local cell): harmonic mean + flux with one reciprocal
+                double Tup = __shfl_up_sync(FULL, T[CPL - 1], 1);
+                double kup = __shfl_up_sync(FULL, kc[CPL - 1], 1);
+                double je[CPL + 1];
 #pragma unroll
                 for (int j = 0; j < CPL; ++j) {
-                    int i = lane * CPL + j;
-                    if (i < N) {
-                        size_t o = (size_t)kt * TG.save_stride + (size_t)i * M + col;
-                        if (saveT) saveT[o] = T[j];
-                        if (saveW) {
-                            const double* c = lcw + loff[j];
-                            double hc = sel_min(relu_bits(H[j]), c[FC_LTH]);
-                            saveW[o] = (hc * c[FC_INVLTH]) * c[FC_THWI];
+                    double T1 = (j == 0) ? Tup : T[j - 1];
+                    double k1 = (j == 0) ? kup : kc[j - 1];
+                    double den = fma(rho[j], k1, kc[j]);
+                    double q = ((T1 - T[j]) * (k1 * kc[j])) * G[j];
+                    je[j] = fma(q, rcp_sel<CUBIC>(den), bflux[j]);   // q == 0 on the bottom edge (G = 0): je = -Qgeo there
+                }
+                if (lane == 0)   // heat_bc.jl:9-17 (Dirichlet) / methods.jl:156 (Neumann)
+                    je[0] = top_dirichlet ? (kc[0] * (vtop - T[0])) * P.ctop : vtop;
+                je[CPL] = __shfl_down_sync(FULL, je[0], 1);
+                if (bflux_next != 0.0 || lane == 31) je[CPL] = bflux_next;               // heat_bc.jl:32-35 / methods.jl:156
+                // ---- divergence, limiter reduction, Euler update
+                double ad[CPL];
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) {
+                    double dH = (je[j] - je[j + 1]) * idk[j];
+                    ad[j] = fabs(dH);
+                    H[j] = fma(dt, dH, H[j]);                                            // basic_solvers.jl:66
+                }
+                // max |dH| over the local cells as a tree (depth log2 CPL instead of CPL dependent compares); NaN is dropped
+#pragma unroll
+                for (int w = 1; w < CPL; w *= 2)
+#pragma unroll
+                    for (int j = 0; j + w < CPL; j += 2 * w) ad[j] = sel_max(ad[j + w], ad[j]);
+                double maxabs = sel_max(ad[0], 0.0);
+                // start the warp reduction (integer REDUX unit) ...
+                unsigned mh = (unsigned)__double2hiint(maxabs), ml = (unsigned)__double2loint(maxabs);
+                unsigned rh = __reduce_max_sync(FULL, mh);
+                unsigned rl = __reduce_max_sync(FULL, mh == rh ? ml : 0u);
+                const double tn = t + dt;
+                ++nsteps;
+                // ... and overlap it with the next step's boundary value and diagnostics
+                vtop = top_value(tn);
+                stage_a();
+                // ---- next dt (basic_solvers.jl:76-77, heat_conduction.jl:183-191, steplimiters.jl:15-18), saveat! clip
+                maxabs = __hiloint2double((int)rh, (int)rl);
+                double mc = sel_min(sel_max(maxabs, 1e-300), 1e300);                     // keeps the reciprocal finite
+                double lim = P.maxdelta * rcp_fast(mc);                                  // 2 Newton steps: correctly rounded 1/x
+                if (maxabs == INFINITY) lim = INFINITY;                                  // |Δmax/inf| = 0 -> "not > 0" -> Inf
+                double dtn = sel_max(sel_min(lim, P.dtmax), P.dtmin);
+                double rem = t_target - tn;
+                dt = (rem > 0.0) ? sel_min(dtn, rem) : dtn;                              // integrator.jl:126-131 (:89 is implied)
+                t = tn;
+        };
+        if (SAVE) {
+            // interior steps of the save interval: the same loop as the plain stepping kernel (with the save code inside the unrolled
+            // loop the kernel spilled 200 bytes; measured 36.4 -> 35.6 ms on the 73 daily saves of the bench window); then the last
+            // step of the interval, which saves first
+#pragma unroll 3
+            while (t + dt < t_target) {
+                if (fkind == 2 && (t < ft_first || t > ft_last)) { status |= 4; break; }     // providers.jl:30-33
+                one_step();
+            }
+            if (!status && t < t_target) {
+                if (fkind == 2 && (t < ft_first || t > ft_last)) status |= 4;
+                else {
+                    {
+                        // Last step of the interval: what the reference SAVES for diagnostic variables is the cache of this (the last)
+                        // RHS evaluation, i.e. T, θw of the state BEFORE the step (problem.jl:67-68 -> Numerics/statevars.jl:81-106
+                        // retrieve(); CGEuler evaluates the tile before u += dt*du, basic_solvers.jl:61-66).  Reproduced verbatim.
+#pragma unroll
+                        for (int j = 0; j < CPL; ++j) {
+                            int i = lane * CPL + j;
+                            if (i < N) {
+                                size_t o = (size_t)kt * TG.save_stride + (size_t)i * M + col;
+                                if (saveT) saveT[o] = T[j];
+                                if (saveW) {
+                                    const double* c = lcw + loff[j];
+                                    double hc = sel_min(relu_bits(H[j]), c[FC_LTH]);
+                                    saveW[o] = (hc * c[FC_INVLTH]) * c[FC_THWI];
+                                }
+                            }
                         }
                     }
+                    one_step();
                 }
             }
-            // ---- edge fluxes (upper edge of every local cell): harmonic mean + flux with one reciprocal
-            double Tup = __shfl_up_sync(FULL, T[CPL - 1], 1);
-            double kup = __shfl_up_sync(FULL, kc[CPL - 1], 1);
-            double je[CPL + 1];
-#pragma unroll
-            for (int j = 0; j < CPL; ++j) {
-                double T1 = (j == 0) ? Tup : T[j - 1];
-                double k1 = (j == 0) ? kup : kc[j - 1];
-                double den = fma(rho[j], k1, kc[j]);
-                double q = ((T1 - T[j]) * (k1 * kc[j])) * G[j];
-                je[j] = fma(q, rcp_sel<CUBIC>(den), bflux[j]);   // q == 0 on the bottom edge (G = 0): je = -Qgeo there
+        } else {
+#pragma unroll 3
+            while (t < t_target) {
+                if (fkind == 2 && (t < ft_first || t > ft_last)) { status |= 4; break; }     // providers.jl:30-33
+                one_step();
             }
-            if (lane == 0)   // heat_bc.jl:9-17 (Dirichlet) / methods.jl:156 (Neumann)
-                je[0] = top_dirichlet ? (kc[0] * (vtop - T[0])) * P.ctop : vtop;
-            je[CPL] = __shfl_down_sync(FULL, je[0], 1);
-            if (bflux_next != 0.0 || lane == 31) je[CPL] = bflux_next;               // heat_bc.jl:32-35 / methods.jl:156
-            // ---- divergence, limiter reduction, Euler update
-            double ad[CPL];
-#pragma unroll
-            for (int j = 0; j < CPL; ++j) {
-                double dH = (je[j] - je[j + 1]) * idk[j];
-                ad[j] = fabs(dH);
-                H[j] = fma(dt, dH, H[j]);                                            // basic_solvers.jl:66
-            }
-            // max |dH| over the local cells as a tree (depth log2 CPL instead of CPL dependent compares); NaN is dropped
-#pragma unroll
-            for (int w = 1; w < CPL; w *= 2)
-#pragma unroll
-                for (int j = 0; j + w < CPL; j += 2 * w) ad[j] = sel_max(ad[j + w], ad[j]);
-            double maxabs = sel_max(ad[0], 0.0);
-            // start the warp reduction (integer REDUX unit) ...
-            unsigned mh = (unsigned)__double2hiint(maxabs), ml = (unsigned)__double2loint(maxabs);
-            unsigned rh = __reduce_max_sync(FULL, mh);
-            unsigned rl = __reduce_max_sync(FULL, mh == rh ? ml : 0u);
-            const double tn = t + dt;
-            ++nsteps;
-            // ... and overlap it with the next step's boundary value and diagnostics
-            vtop = top_value(tn);
-            stage_a();
-            // ---- next dt (basic_solvers.jl:76-77, heat_conduction.jl:183-191, steplimiters.jl:15-18), saveat! clip
-            maxabs = __hiloint2double((int)rh, (int)rl);
-            double mc = sel_min(sel_max(maxabs, 1e-300), 1e300);                     // keeps the reciprocal finite
-            double lim = P.maxdelta * rcp_fast(mc);                                  // 2 Newton steps: correctly rounded 1/x
-            if (maxabs == INFINITY) lim = INFINITY;                                  // |Δmax/inf| = 0 -> "not > 0" -> Inf
-            double dtn = sel_max(sel_min(lim, P.dtmax), P.dtmin);
-            double rem = t_target - tn;
-            dt = (rem > 0.0) ? sel_min(dtn, rem) : dtn;                              // integrator.jl:126-131 (:89 is implied)
-            t = tn;
         }
         if (status) break;
         }
