@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(128) k_salt_euler(const __grid_constant__ Dev 
                 double TK = T[j] + 273.15;
                 double psi, dpsi_dT, dpsi_dc;
                 if (Tstar - TK >= 0.0) {
-                    double rT = rcp_fast(Tstar);
+                    double rT = rcp_fast3(Tstar);
                     double cfac = Lg * rT;
                     psi = psi0[j] + cfac * (TK - Tstar);
                     dpsi_dT = cfac;
@@ -136,11 +136,11 @@ __global__ void __launch_bounds__(128) k_salt_euler(const __grid_constant__ Dev 
                 int s = j * 32 + lane;
                 double w1 = sW1[s], w2 = sW2[s], idx = sG[s];        // idx = 1/Δxc
                 // harmonicmean (math.jl:41): (w1+w2)/(w1/k1 + w2/k2) = (w1+w2) k1 k2 / (w1 k2 + w2 k1), one reciprocal each
-                ke[j] = ((w1 + w2) * (k1 * kc[j])) * rcp_fast(fma(w1, kc[j], w2 * k1));
-                de[j] = ((w1 + w2) * (d1 * dsm[j])) * rcp_fast(fma(w1, dsm[j], w2 * d1));
+                ke[j] = ((w1 + w2) * (k1 * kc[j])) * rcp_fast3(fma(w1, kc[j], w2 * k1));
+                de[j] = ((w1 + w2) * (d1 * dsm[j])) * rcp_fast3(fma(w1, dsm[j], w2 * d1));
                 jH[j] = -ke[j] * (T[j] - T1) * idx;                  // math.jl:141
                 jc[j] = -de[j] * (c[j] - c1) * idx;
-                if (idx == 0.0) { jH[j] = 0.0; jc[j] = 0.0; }
+                // idx == 0 on non-interior edges: the fluxes vanish there without a select
             }
             if (lane == 0) {
                 ke[0] = kc[0]; de[0] = dsm[0];
@@ -150,7 +150,8 @@ __global__ void __launch_bounds__(128) k_salt_euler(const __grid_constant__ Dev 
             jH[CPL] = __shfl_down_sync(FULL, jH[0], 1);
             jc[CPL] = __shfl_down_sync(FULL, jc[0], 1);
             double dTv[CPL], dcv[CPL], dHv[CPL], dcF[CPL];
-            double lim = INFINITY, limh = INFINITY;
+            double rate_s = 0.0, rate_c = 0.0, rate_h = 0.0;
+            bool nonfinite = false;
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
                 double jHl = jH[j + 1], jcl = jc[j + 1];
@@ -162,18 +163,20 @@ __global__ void __launch_bounds__(128) k_salt_euler(const __grid_constant__ Dev 
                 double A = dHdT[j], B = P.L * dthc[j], Dd = dHv[j];
                 double E = thw[j] + c[j] * dthc[j], F = c[j] * dthT[j], Gg = dcF[j];
                 double det = A * E - B * F;
-                double rdet = rcp_fast(det);
+                double rdet = rcp_fast3(det);
                 dTv[j] = (-B * Gg + Dd * E) * rdet;
                 dcv[j] = (-F * Dd + A * Gg) * rdet;
                 if (lane * CPL + j < N) {
-                    double dx = sDk[s];
-                    double dts = S.courant * rcp_fast(de[j]) * (dx * dx);                       // salt_diffusion.jl:112-119
-                    double adc = fabs(dcv[j]);
-                    double dtc = (adc > 0.0) ? S.dc_max * rcp_fast(adc) : INFINITY;              // dc_max/|dc| (Inf for dc == 0)
-                    if (dts < lim) lim = dts;                                                   // NaN is skipped, as by fmin
-                    if (dtc < lim) lim = dtc;
-                    double dth = S.heat_courant * (dHdT[j] * rcp_fast(kc[j])) * (dx * dx);      // heat_conduction.jl:170-178
-                    if (dth < limh) limh = dth;
+                    // the limiters are minima of quotients with a warp-uniform numerator: carry the MAXIMUM of the per-cell rates and
+                    // take one reciprocal per limiter after the warp reduction (was three reciprocals per cell and step)
+                    double idx2 = sInvDk[s] * sInvDk[s];
+                    double rs = de[j] * idx2;                                                   // salt_diffusion.jl:112-119: dt = courant dx^2 / ds
+                    double adc = fabs(dcv[j]);                                                  // dt = dc_max / |dc| (Inf for dc == 0)
+                    double rh = (kc[j] * idx2) * rcp_fast3(dHdT[j]);                            // heat_conduction.jl:170-178: dt = courant dHdT dx^2 / k
+                    if (rs > rate_s) rate_s = rs;                                               // NaN is skipped, as by fmin
+                    if (adc > rate_c) rate_c = adc;
+                    if (rh > rate_h) rate_h = rh;
+                    nonfinite |= !(rs == rs) || !(adc == adc) || !(rh == rh) || rs < 0.0 || rh < 0.0;
                 }
             }
             if (DIAG) {
@@ -214,11 +217,11 @@ __global__ void __launch_bounds__(128) k_salt_euler(const __grid_constant__ Dev 
             ++nsteps;
             // warp minima through the integer REDUX unit (positive doubles order like their bit patterns); a non-positive or
             // NaN limit is the reference's "dt <= 0" assertion (tile.jl:174)
-            const bool bad = __any_sync(FULL, !(lim > 0.0) || !(limh > 0.0));
-            lim = warp_min_pos(lim > 0.0 ? lim : INFINITY);
-            limh = warp_min_pos(limh > 0.0 ? limh : INFINITY);
-            lim = sel_min(lim, limh);
-            if (bad) { status |= 8; lim = 0.0; }
+            const bool bad = __any_sync(FULL, nonfinite);
+            rate_s = warp_max_nonneg(rate_s); rate_c = warp_max_nonneg(rate_c); rate_h = warp_max_nonneg(rate_h);
+            auto quot = [](double num, double rate) { return rate > 0.0 ? num * rcp_fast(rate) : INFINITY; };   // rate 0: no limit
+            double lim = sel_min(sel_min(quot(S.courant, rate_s), quot(S.dc_max, rate_c)), quot(S.heat_courant, rate_h));
+            if (bad || !(lim > 0.0)) { status |= 8; lim = 0.0; }
             double dtn = sel_max(sel_min(lim, P.dtmax), P.dtmin);
             if (t < t_target) dtn = sel_min(dtn, t_target - t);
             dt = sel_min(dtn, P.dtmax);
