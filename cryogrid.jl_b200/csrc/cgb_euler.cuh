@@ -114,7 +114,7 @@ __device__ __forceinline__ void sfcc_newton_solve(const double* lc, double L, do
         double r = (T * C + L * thw) - H;
         dHdT = C + dth * (L + T * dC);                 // heat_methods.jl:105
         if (r > 0.0) hi = T; else lo = T;
-        double Tn = EXACT ? T - r / dHdT : fma(-r, rcp_fast(dHdT), T);
+        double Tn = EXACT ? T - r / dHdT : fma(-r, rcp_fast1(dHdT), T);   // a Newton correction: 1e-13 relative is plenty
         // a Newton step is taken if it falls strictly inside the bracket, or ON its end when it is a converged step (the
         // strict test alone would bisect there; the inclusive test alone lets Newton 2-cycle between the bracket ends).
         // NaN -> bisect.

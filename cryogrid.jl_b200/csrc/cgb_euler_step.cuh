@@ -179,7 +179,7 @@ __global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, const
                 int s = j * 32 + lane;
                 double den = fma(sW2[s], k1, sW1[s] * kc[j]);
                 double kk = k1 * kc[j];
-                je[j] = -(((T[j] - T1) * kk) * sG[s]) * rcp_fast(den);
+                je[j] = -(((T[j] - T1) * kk) * sG[s]) * rcp_fast3(den);
             }
             // Top: Dirichlet -k[1](T[1]-T_ub)/(Δk[1]/2) (heat_bc.jl:9-17) ; Neumann: value (methods.jl:156)
             if (lane == 0) je[0] = (P.top_kind == 0) ? -(kc[0] * (T[0] - vtop)) * P.ctop : vtop;
@@ -203,7 +203,7 @@ __global__ void CGB_STEP_BOUNDS k_heat_step(const __grid_constant__ Dev P, const
                 ad[j] = fabs(dH);
                 double inc = dt * dH;
                 H[j] += inc;                                                          // u += dt*du (basic_solvers.jl:66)
-                if (MODE == 0 || MODE == 2) T[j] = fma(inc, rcp_fast(dHdT[j]), T[j]); // first-order predictor = next Newton seed
+                if (MODE == 0 || MODE == 2) T[j] = fma(inc, rcp_fast1(dHdT[j]), T[j]); // first-order predictor = next Newton seed
             }
 #pragma unroll
             for (int w = 1; w < CPL; w *= 2)
