@@ -40,7 +40,7 @@ struct ColumnCurve {
         return fma(d, pb, thres);
     }
     // θw and dθw/du by the closed form (outside the table).  Out of line on purpose: it is called from the seven pass-2 bodies and
-    // hardly ever runs; inlined, the step loop was 8 200 SASS instructions instead of 3 300 and 6-9 % slower (instruction fetch).
+    // hardly ever runs; inlined, the kernel was 9 900 SASS instructions instead of 8 100 and 6-9 % slower (instruction fetch).
     __device__ __noinline__ double eval(double u, double& dthdu) const
     {
         const double x = alpha * fma(cfac, u, apsi0);
@@ -58,7 +58,8 @@ struct ColumnCurve {
 };
 
 // one bin: interpolating polynomial at the 8 Chebyshev nodes of r in [-1/32, 1/32], u = 2^E (c_k + r), as monomials in r
-__device__ __forceinline__ void nt_fit_bin(const ColumnCurve& f, int E, int k, double* __restrict__ row)
+template <class F>
+__device__ __forceinline__ void nt_fit_bin(const F& f, int E, int k, double* __restrict__ row)
 {
     constexpr double NT_NODE[8] = NT_NODES;
     const double scale = __hiloint2double((E + 1023) << 20, 0);          // 2^E

@@ -8,8 +8,38 @@
 #pragma once
 #include "cgb_handle.h"
 #include "cgb_euler.cuh"
+#include "cgb_euler_newton_tab.cuh"     // nt_fit_bin: degree-7 Chebyshev interpolation of one log-spaced bin
 
 namespace cgb {
+
+// Per-column table of the van Genuchten retention function g(x) = (1 + x^n)^-m over x = alpha |psi| (stepping kernel only): the same
+// construction as the per-column curve tables of k_heat_newton_tab -- log-spaced bins from the bits of x (16 per octave,
+// 2^ST_EMIN <= x < 2^(ST_EMAX+1)), a degree-7 polynomial in the mantissa remainder per bin, fitted by the warp when it picks up a
+// column.  θw = θres + (θsat - θres) g(x) and dθw/dψ = -(θsat - θres) alpha g'(x): porosity stays outside the table (it varies with
+// depth).  Replaces two exp/log pairs, two reciprocals and the derivative algebra (~90 FP64 instructions) by 4 x LDS.128 + 13 FMAs.
+constexpr int ST_EMIN = -8, ST_EMAX = 15;
+constexpr int ST_ROWS = (ST_EMAX + 1 - ST_EMIN) * 16;          // 384
+constexpr int ST_STRIDE = 8;                                    // 64-byte rows (8 warps x 24 KB per SM)
+constexpr int ST_IDX_BASE = (ST_EMIN + 1023) << 4;
+
+struct VgRetention {
+    double n, m;
+    __device__ __forceinline__ double operator()(double x) const
+    {
+        double xn, pb;
+        vg_powers_body<true>(x, n, m, xn, pb);
+        return pb;
+    }
+};
+
+// closed form outside the table (|psi| below 4 mm / alpha or above 65 km / alpha, psi > 0): out of line, it hardly ever runs
+__device__ __noinline__ double vg_theta_fallback(double psi, double thsat, double thres, double alpha, double n, double m, double* dth)
+{
+    double d;
+    const double th = vg_theta<true>(psi, thsat, thres, alpha, n, m, d);
+    *dth = d;
+    return th;
+}
 
 struct SaltDiag {
     double *thw, *dthwdT, *dthwdc, *C, *dHdT, *H, *kc;   // [N*M]
@@ -29,6 +59,7 @@ __global__ void __launch_bounds__(128) k_salt_euler(const __grid_constant__ Dev 
     const int lane = threadIdx.x & 31;
     const int N = P.N;
     const long long M = P.M;
+    double* __restrict__ tab = sG + CPL * 32 + (size_t)(threadIdx.x >> 5) * (ST_ROWS * ST_STRIDE);     // this warp's retention table (!DIAG)
     if (!DIAG) vgtab_init();                              // exp / log tables of the van Genuchten powers (stepping only)
     for (int s = threadIdx.x; s < CPL * 32; s += blockDim.x) {
         int j = s >> 5, ln = s & 31;
@@ -75,6 +106,13 @@ __global__ void __launch_bounds__(128) k_salt_euler(const __grid_constant__ Dev 
                 Kb[j] = P.sk_i * thwi[j] + P.sk_a * tha + P.sk_m * thm + P.sk_o * tho;
             }
         }
+        const bool use_tab = !DIAG && Sn != 2.0;                       // n == 2 is a single rsqrt already
+        if (use_tab) {
+            VgRetention g; g.n = Sn; g.m = m;
+            __syncwarp();
+            for (int b = lane; b < ST_ROWS; b += 32) nt_fit_bin(g, ST_EMIN + (b >> 4), b & 15, tab + b * ST_STRIDE);
+            __syncwarp();
+        }
         double T[CPL], c[CPL];
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
@@ -115,7 +153,44 @@ __global__ void __launch_bounds__(128) k_salt_euler(const __grid_constant__ Dev 
                 } else { psi = psi0[j]; dpsi_dT = 0.0; dpsi_dc = 0.0; }
                 double dth;
                 double thsat = sel_max(Ssat * por[j], por[j]);
-                thw[j] = vg_theta<!DIAG>(psi, thsat, Sthres, Salpha, Sn, m, dth);
+                if (use_tab) {
+                    const double x = Salpha * fabs(psi);
+                    const int xh = __double2hiint(x), xl = __double2loint(x);
+                    const int bin = (xh >> 16) - ST_IDX_BASE;
+                    if (psi <= 0.0 && (unsigned)bin < (unsigned)ST_ROWS) {
+                        const double mant = __hiloint2double((xh & 0x000fffff) | 0x3ff00000, xl);
+                        const double cen = __hiloint2double(0x3ff08000 | (xh & 0x000f0000), 0);
+                        const double r = mant - cen;
+                        const double* cf = tab + bin * ST_STRIDE;
+                        const double2 c01 = *reinterpret_cast<const double2*>(cf), c23 = *reinterpret_cast<const double2*>(cf + 2);
+                        const double2 c45 = *reinterpret_cast<const double2*>(cf + 4), c67 = *reinterpret_cast<const double2*>(cf + 6);
+                        double p = fma(c67.y, r, c67.x), q = c67.y;           // Horner with the derivative by synthetic division
+                        q = fma(q, r, p); p = fma(p, r, c45.y);
+                        q = fma(q, r, p); p = fma(p, r, c45.x);
+                        q = fma(q, r, p); p = fma(p, r, c23.y);
+                        q = fma(q, r, p); p = fma(p, r, c23.x);
+                        q = fma(q, r, p); p = fma(p, r, c01.y);
+                        q = fma(q, r, p); p = fma(p, r, c01.x);
+                        const double inv_scale = __hiloint2double((2046 - ((xh >> 20) & 0x7ff)) << 20, 0);      // 2^-E
+                        const double dsat = thsat - Sthres;
+                        thw[j] = fma(dsat, p, Sthres);
+                        dth = -(dsat * Salpha) * (q * inv_scale);             // dθ/dψ = -Δθ alpha g'(x)
+                    } else if (!(x > 0.0) || psi > 0.0) {                     // psi0 = 0 above T* (saturated): θw = θsat
+                        thw[j] = thsat; dth = 0.0;
+                    } else {
+                        thw[j] = vg_theta_fallback(psi, thsat, Sthres, Salpha, Sn, m, &dth);
+                    }
+                } else if (DIAG) {
+                    thw[j] = vg_theta<false>(psi, thsat, Sthres, Salpha, Sn, m, dth);
+                } else if (psi <= 0.0) {
+                    // stepping with n == 2 (m = 1/2): θ = θres + Δθ (1+x²)^(-1/2), dθ/dψ = Δθ α x (1+x²)^(-3/2) -- one rsqrt, no table
+                    const double x = fabs(-Salpha * psi), dsat = thsat - Sthres;
+                    const double rs = rsqrt_fast(fma(x, x, 1.0));
+                    dth = dsat * Salpha * x * (rs * rs * rs);
+                    thw[j] = fma(dsat, rs, Sthres);
+                } else {
+                    thw[j] = thsat; dth = 0.0;
+                }
                 dthT[j] = dth * dpsi_dT;
                 dthc[j] = dth * dpsi_dc;
                 Cc[j] = fma(dC, thw[j], Cb[j]);
@@ -285,7 +360,7 @@ static int salt_launch_t(cgb_handle* h, double t_target, const cgb::SaltDiag& D)
 {
     using namespace cgb;
     auto kern = k_salt_euler<CPL, DIAG>;
-    size_t smem = (size_t)(5 * CPL * 32) * sizeof(double);
+    size_t smem = (size_t)(5 * CPL * 32 + (DIAG ? 0 : 4 * ST_ROWS * ST_STRIDE)) * sizeof(double);
     int blocks_per_sm = 0;
     CUDA_TRY(h, cgb_prepare_kernel(h, (const void*)kern, smem, &blocks_per_sm));
     long long grid = std::min<long long>((h->M + 3) / 4, (long long)h->num_sms * blocks_per_sm);

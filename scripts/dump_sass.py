@@ -71,6 +71,22 @@ def hot_loop(lines):
             tgt = int(m.group(1), 16)
             if tgt <= a and tgt in addr_index:
                 loops.append((addr_index[tgt], i))
+    # per-column set-up loops (the table fits of k_heat_newton_tab / k_salt_euler) hold a lot of FP64 work but are not step loops:
+    # a step loop exchanges neighbours or reduces the limiter across the warp
+    def has_warp_op(lo, hi):
+        return any(re.match(r"(@!?U?P\d+\s+)?(SHFL|REDUX|CREDUX)", t) for _, t in lines[lo:hi + 1])
+    warp_loops = [l for l in loops if has_warp_op(*l)]
+    if warp_loops:
+        # several back edges to one header (an unrolled loop) are ONE loop: keep the widest range per header
+        by_head = {}
+        for lo, hi in warp_loops:
+            by_head[lo] = max(by_head.get(lo, hi), hi)
+        merged = sorted(by_head.items())
+        fp = {l: sum(1 for _, t in lines[l[0]:l[1] + 1] if classify(t) == "fp64 pipe") for l in merged}
+        # innermost: contains no other warp-op loop with a fair amount of FP64 work; of those, the one with the most FP64
+        inner = [l for l in merged if not any(o != l and l[0] <= o[0] and o[1] <= l[1] and fp[o] >= 20 for o in merged)]
+        inner = [l for l in inner if fp[l] >= 20] or inner
+        return max(inner, key=lambda l: fp[l])
     best, score = None, -1
     for lo, hi in loops:
         nfp = sum(1 for _, t in lines[lo:hi + 1] if classify(t) == "fp64 pipe")

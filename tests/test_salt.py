@@ -151,3 +151,40 @@ def test_salt_per_column_parameters_forcing_and_saveat(orc):
     st, _ = eng.status()
     assert np.all(st & 4)
     eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [2.0, 1.45, 2.03, 3.1])
+def test_salt_retention_table_and_n2_path(orc, n):
+    # The stepping kernel evaluates the van Genuchten retention function from a per-column table fitted by the warp (n != 2) or by
+    # one rsqrt (n == 2); the diagnostics kernel and the oracle use the closed form.  One day from a state that spans thawed
+    # cells (psi = 0), the freezing front and cold cells, against the oracle: equal step counts, 1e-9 K / 1e-9 relative in c.
+    M = 6
+    rng = np.random.default_rng(3)
+    tile = cg.SalineTile(sfcc=cg.DallAmicoSalt(swrc=cg.VanGenuchten(alpha=rng.uniform(1.0, 6.0, M), n=n)),
+                         salt_bc=cg.SaltGradient(rng.uniform(600.0, 1000.0, M), 0), ncolumns=M)
+    u0 = tile.initialcondition()
+    u0[0] += rng.uniform(-25.0, 2.5, u0[0].shape)
+    u0[1] += rng.uniform(0.0, 800.0, u0[1].shape)
+    eng = cg.SaltEngine(tile)
+    eng.set_state(u0, 0.0)
+    targets = (3600.0, 86400.0)
+    for tt in targets:
+        eng.advance_to(tt)
+    u, t, dt = eng.get_state(with_time=True)
+    st, steps = eng.status()
+    assert not st.any()
+    worst = 0.0
+    for c in range(M):
+        oc = orc.OracleSaltColumn(tile, c)
+        T, cc, tr, dtr, ns = u0[0, :, c], u0[1, :, c], 0.0, 60.0, 0
+        for tt in targets:
+            T, cc, tr, dtr, n2, s2 = oc.advance(T, cc, tr, dtr, tt)
+            assert s2 == 0
+            ns += n2
+        assert t[c] == tr and steps[c] == ns, (c, steps[c], ns)
+        eT, ec = np.max(np.abs(u[0, :, c] - T)), np.max(np.abs(u[1, :, c] - cc) / np.maximum(1.0, np.abs(cc)))
+        assert eT < 1e-9 and ec < 1e-9, (c, eT, ec)
+        worst = max(worst, eT)
+    print(f"salt, van Genuchten n = {n}: 1 day vs oracle, max |dT| {worst:.2e} K")
+    eng.close()
