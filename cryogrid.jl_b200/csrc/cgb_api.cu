@@ -974,10 +974,19 @@ __global__ void __launch_bounds__(128) k_thawdepth(const double* __restrict__ T,
     if (col >= M) return;
     int i_frozen = -1, i_thawed = -1;
     double Tf = 0.0, Tt = 0.0;
-    for (int i = 0; i < N && (i_frozen < 0 || i_thawed < 0); ++i) {
-        double v = T[(size_t)i * M + col];
-        if (i_frozen < 0 && v <= 0.0) { i_frozen = i; Tf = v; }
-        if (i_thawed < 0 && v > 0.0) { i_thawed = i; Tt = v; }
+    // eight cells per round: the loads of a round are independent (one thread per column is latency bound otherwise: a batch of
+    // 10^4 columns puts ~70 threads on an SM, and a scan that exits after every cell pays one DRAM round trip per cell)
+    for (int i0 = 0; i0 < N && (i_frozen < 0 || i_thawed < 0); i0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (i0 + k < N) ? __ldcs(T + (size_t)(i0 + k) * M + col) : 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (i0 + k < N) {
+                if (i_frozen < 0 && v[k] <= 0.0) { i_frozen = i0 + k; Tf = v[k]; }
+                if (i_thawed < 0 && v[k] > 0.0) { i_thawed = i0 + k; Tt = v[k]; }
+            }
+        }
     }
     double td;
     if (i_thawed >= 0 && i_frozen >= 0 && i_thawed < i_frozen) {
