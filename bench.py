@@ -335,7 +335,7 @@ def run_reference(args):
     orc.use_timing_copy(True)
     nmax = host_threads()
     ncol = max(args.cpu_columns, 2 * nmax)
-    tile = make_tile(ncol, 400, seed=1)
+    tile = make_tile(ncol, 2 + (args.steps + args.warmup) * args.days_per_step, seed=1)      # forcing covers every step of the run
     H0 = cg.initialcondition(tile)
     N = tile.grid.ncells
     cols = np.arange(ncol)

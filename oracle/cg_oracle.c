@@ -354,14 +354,18 @@ double cg_nfactor(double Tair, double nf, double nt)
  * Column RHS
  * ---------------------------------------------------------------------------------------- */
 
+#ifdef CG_ORACLE_FAST
+/* timing copy: the grid arrays of a work block are computed once per (grid, work block), not once per RHS evaluation.  The cache is
+ * keyed by address, so work_alloc() -- whose fresh, zeroed block may land on the address of the one just freed -- resets it. */
+static __thread const double* cg_fast_last_edges = NULL;
+static __thread const double* cg_fast_last_zc = NULL;
+#endif
+
 void cg_work_grid(const cg_column* col, cg_work* w)
 {
 #ifdef CG_ORACLE_FAST
-    /* timing copy: the grid arrays of a work block are computed once per (grid, work block), not once per RHS evaluation */
-    static __thread const double* last_edges = NULL;
-    static __thread const double* last_zc = NULL;
-    if (last_edges == col->edges && last_zc == w->zc) return;
-    last_edges = col->edges; last_zc = w->zc;
+    if (cg_fast_last_edges == col->edges && cg_fast_last_zc == w->zc) return;
+    cg_fast_last_edges = col->edges; cg_fast_last_zc = w->zc;
 #endif
     cg_grid(col->edges, col->n + 1, w->zc, w->dk, w->dxc);
 }
@@ -848,6 +852,9 @@ static void work_alloc(cg_work* w, int n, double** block)
 {
     double* p = (double*)calloc((size_t)(17 * (n + 1)), sizeof(double));
     *block = p;
+#ifdef CG_ORACLE_FAST
+    cg_fast_last_edges = NULL; cg_fast_last_zc = NULL;
+#endif
     w->T = p; p += n; w->thw = p; p += n; w->C = p; p += n; w->dHdT = p; p += n; w->dthwdT = p; p += n;
     w->kc = p; p += n; w->k = p; p += n + 1; w->jH = p; p += n + 1; w->dH = p; p += n;
     w->an = p; p += n; w->as = p; p += n; w->ap = p; p += n; w->bp = p; p += n;
