@@ -342,14 +342,12 @@ def run_reference(args):
     prepared = orc.batch_columns(tile, cols)
     cores, thread_rates = pick_threads(tile, H0, cols, prepared, nmax)
     H = np.ascontiguousarray(H0.T); t = np.zeros(ncol); dt = np.full(ncol, 60.0)
-    # calibrate the per-step sample so that the whole run stays within ~2 minutes
-    t0 = time.perf_counter()
-    orc.cgeuler_advance_batch(tile, cols, H, t, dt, 0.5 * DAY, nthreads=cores, prepared=prepared)
-    t0 = time.perf_counter()
+    # size the per-step sample so that the whole run stays within ~2 minutes: the limiter-bound seasons of cfg2 take ~400 steps per
+    # column and simulated day (the frozen ones 24), the throughput is the one just measured at the chosen thread count
     orc.cgeuler_advance_batch(tile, cols, H, t, dt, 1.0 * DAY, nthreads=cores, prepared=prepared)
-    per_day = (time.perf_counter() - t0) / 0.5
-    budget = 60.0 / max(args.steps + args.warmup, 1)
-    days = max(0.02, min(args.days_per_step, budget / max(per_day, 1e-4)))
+    per_day = 400.0 * ncol / max(thread_rates[cores], 1.0)
+    budget = 120.0 / max(args.steps + args.warmup, 1)
+    days = max(0.5, min(args.days_per_step, budget / max(per_day, 1e-6)))
     cur = 1.0
     for _ in range(args.warmup):
         cur += days
