@@ -62,14 +62,14 @@ def peaks():
 
 def measured_traffic():
     """DRAM bytes per launch of the headline kernel from the committed `ncu --set full` capture of THIS bench command on the
-    final build (profiles/r2_ncu_bench_fast_kernel.json, written by scripts/ncu_traffic.py); None when there is no capture."""
-    path = os.path.join(ROOT, "profiles", "r2_ncu_bench_fast_kernel.json")
+    final build (profiles/r3j_ncu_bench_fast_kernel.json, written by scripts/ncu_traffic.py); None when there is no capture."""
+    path = os.path.join(ROOT, "profiles", "r3j_ncu_bench_fast_kernel.json")
     try:
         with open(path) as f:
             d = json.load(f)
         return (int(d["dram_bytes_read"] + d["dram_bytes_write"]),
                 f"dram__bytes_read.sum + dram__bytes_write.sum of the longest launch of {d['kernel'].split('(')[0]} in an ncu --set full capture of "
-                f"`{d['command']}` (profiles/r2_ncu_bench_fast_kernel.json)", d.get("fp64_pipe_pct"))
+                f"`{d['command']}` (profiles/r3j_ncu_bench_fast_kernel.json)", d.get("fp64_pipe_pct"))
     except Exception:
         return None, "no ncu --set full capture of the bench command committed", None
 

@@ -3,7 +3,7 @@
 file bench.py cites for `roofline.traffic`:
 
     ncu -i gpurun_out/<report>.ncu-rep --page raw --csv > /tmp/raw.csv
-    python scripts/ncu_traffic.py /tmp/raw.csv k_heat_euler_fast "<the profiled command>" profiles/r2_ncu_bench_fast_kernel.json
+    python scripts/ncu_traffic.py /tmp/raw.csv k_heat_euler_fast "<the profiled command>" profiles/r3j_ncu_bench_fast_kernel.json
 """
 import csv
 import json
