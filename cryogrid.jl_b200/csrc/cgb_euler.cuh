@@ -163,14 +163,12 @@ __device__ __forceinline__ void freezethaw_body(const Dev& P, const double* lc, 
         dHdT = C + dth * (P.L + T * dC);   // heat_methods.jl:105
     } else if ((kind & 0xff) == 0) {
         // FreeWater: heat_conduction.jl:18-57 (θw = clamp(H/Lθ,0,1) θtot; T piecewise; ∂H∂T = 1e8 at T == 0)
-        double x = H * lc[LC_INVLTHTOT];
-        double xc = sel_min(sel_max(x, 0.0), 1.0);
-        thw = xc * lc[LC_THTOT];
+        // One clamp instead of two clamps and a three-way select (the form of the FreeWater fast kernel): hc = clamp(H, 0, Lθ) is the
+        // latent part of H, θw = hc/(Lθ) θtot, and T = (H - hc)/C is H/C below, EXACTLY 0 inside and (H - Lθ)/C above the phase change.
+        double hc = sel_min(relu_bits(H), lc[LC_LTH]);
+        thw = (hc * lc[LC_INVLTHTOT]) * lc[LC_THTOT];
         C = fma(dC, thw, lc[LC_CB]);
-        double invC = rcp_fast(C);
-        double Lth = lc[LC_LTH];
-        double num = (H < 0.0) ? H : ((H >= Lth) ? (H - Lth) : 0.0);
-        T = num * invC;
+        T = (H - hc) * rcp_fast3(C);
         dHdT = (T == 0.0) ? 1e8 : C;
         dth = 0.0;
     } else if (((kind >> 8) & 0xff) == 0) {
